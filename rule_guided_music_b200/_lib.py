@@ -1,0 +1,87 @@
+"""ctypes binding of librgm_b200.so (C ABI declared in include/rgm_b200.h).
+
+There is deliberately no fallback: if the shared library is missing or the device is not sm_100, every call
+raises.  The library is built in-tree by ``__graft_entry__.build()`` (``make -C rule_guided_music_b200/csrc``).
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "librgm_b200.so")
+
+_lib = None
+
+c_void_p = ctypes.c_void_p
+c_int = ctypes.c_int
+c_float = ctypes.c_float
+c_double = ctypes.c_double
+c_ll = ctypes.c_longlong
+
+
+class RgmError(RuntimeError):
+    pass
+
+
+def _declare(lib):
+    lib.rgm_last_error.restype = ctypes.c_char_p
+    lib.rgm_last_error.argtypes = []
+    lib.rgm_version.restype = c_int
+    lib.rgm_launch_count.restype = ctypes.c_ulonglong
+    lib.rgm_check_device.restype = c_int
+    for name, args in _SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = c_int
+        fn.argtypes = args
+
+
+# name -> argtypes; every function returns int (0 = ok)
+_SIGNATURES = {
+    "rgm_gemm_f16": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
+    "rgm_conv_f16": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
+                     c_int, c_void_p, c_void_p],
+    "rgm_pack_conv_weight": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p],
+}
+
+
+def lib():
+    """Load the shared library once; raise loudly when it is absent."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RgmError(
+                f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(the B200 path has no CPU or PyTorch fallback)")
+        _lib = ctypes.CDLL(LIB_PATH)
+        _declare(_lib)
+    return _lib
+
+
+def exported_symbols():
+    """Names every include/rgm_b200.h entry point must resolve to (used by the CPU-side ABI test)."""
+    return ["rgm_last_error", "rgm_version", "rgm_launch_count", "rgm_check_device"] + list(_SIGNATURES)
+
+
+def check(rc):
+    if rc != 0:
+        raise RgmError(lib().rgm_last_error().decode("utf-8", "replace"))
+
+
+def call(name, *args):
+    check(getattr(lib(), name)(*args))
+
+
+def ptr(t):
+    """Raw device pointer of a torch tensor (or None)."""
+    if t is None:
+        return None
+    return c_void_p(t.data_ptr())
+
+
+def stream_ptr():
+    import torch
+
+    return c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def launch_count():
+    return int(lib().rgm_launch_count())

@@ -1,0 +1,160 @@
+// C ABI: library-level entry points and the GEMM / convolution building blocks (include/rgm_b200.h).
+#include <cstdio>
+#include <cstdlib>
+#include <string>
+
+#include "../../include/rgm_b200.h"
+#include "api_util.h"
+#include "gemm_host.h"
+
+namespace rgm {
+
+thread_local std::string g_last_error;
+
+int set_error(const std::string& m) {
+  g_last_error = m;
+  return -1;
+}
+int check_cuda(cudaError_t e, const char* what) {
+  if (e == cudaSuccess) return 0;
+  return set_error(std::string(what) + ": " + cudaGetErrorString(e));
+}
+
+std::atomic<unsigned long long> g_aux_launches{0};
+
+// weight fp32 [Cout,Cin,kh,kw] -> packed fp16 [rows][taps*cin_pad]
+__global__ void pack_conv_weight_kernel(const float* __restrict__ w, __half* __restrict__ out, int Cout, int Cin,
+                                        int cout_pad, int cin_pad, int kind) {
+  const int taps = kind == 0 ? 1 : (kind == 1 ? 9 : 4);
+  const int npar = kind == 2 ? 4 : 1;
+  const long long K = (long long)taps * cin_pad;
+  const long long total = (long long)npar * cout_pad * K;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int ci = (int)(i % cin_pad);
+    const int t = (int)((i / cin_pad) % taps);
+    const long long row = i / K;
+    const int co = (int)(row % cout_pad);
+    const int par = (int)(row / cout_pad);
+    float v = 0.f;
+    if (co < Cout && ci < Cin) {
+      if (kind == 0) {
+        v = w[(long long)co * Cin + ci];
+      } else if (kind == 1) {
+        v = w[((long long)co * Cin + ci) * 9 + t];
+      } else {
+        // nearest-2x upsample then 3x3: output pixel (2i+ph, 2j+pw) reads low-res rows {i+ph-1, i+ph}; tap a = 0/1.
+        // ph = 0: a=0 <- ky {0}, a=1 <- ky {1,2};  ph = 1: a=0 <- ky {0,1}, a=1 <- ky {2}.   Same for columns.
+        const int ph = par >> 1, pw = par & 1, a = t >> 1, b = t & 1;
+        const int ky0 = ph == 0 ? (a == 0 ? 0 : 1) : (a == 0 ? 0 : 2);
+        const int ky1 = ph == 0 ? (a == 0 ? 0 : 2) : (a == 0 ? 1 : 2);
+        const int kx0 = pw == 0 ? (b == 0 ? 0 : 1) : (b == 0 ? 0 : 2);
+        const int kx1 = pw == 0 ? (b == 0 ? 0 : 2) : (b == 0 ? 1 : 2);
+        const float* wp = w + ((long long)co * Cin + ci) * 9;
+        for (int ky = ky0; ky <= ky1; ++ky)
+          for (int kx = kx0; kx <= kx1; ++kx) v += wp[ky * 3 + kx];
+      }
+    }
+    out[i] = __float2half_rn(v);
+  }
+}
+
+}  // namespace rgm
+
+using namespace rgm;
+
+extern "C" {
+
+const char* rgm_last_error(void) { return g_last_error.c_str(); }
+int rgm_version(void) { return 100; }
+unsigned long long rgm_launch_count(void) { return gemm_launch_count() + g_aux_launches.load(); }
+
+int rgm_check_device(void) {
+  // cudaGetDeviceProperties costs milliseconds: query each device once.
+  static std::atomic<int> ok_mask{0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return set_error("rgm_b200: no CUDA device (this library has no CPU path)");
+  if (dev < 31 && (ok_mask.load(std::memory_order_relaxed) >> dev) & 1) return 0;
+  int major = 0, minor = 0;
+  if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess ||
+      cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev) != cudaSuccess)
+    return set_error("rgm_b200: cannot query the device");
+  if (major != 10) {
+    char buf[160];
+    snprintf(buf, sizeof buf, "rgm_b200: device %d is sm_%d%d; this library is built for sm_100a only", dev, major,
+             minor);
+    return set_error(buf);
+  }
+  if (dev < 31) ok_mask.fetch_or(1 << dev);
+  return 0;
+}
+
+int rgm_gemm_f16(const void* a16, const void* b16, const float* bias, float* out32, int M, int N, int K, int block_n,
+                 void* stream) {
+  if (rgm_check_device()) return -1;
+  GemmDesc d;
+  d.A = static_cast<const __half*>(a16);
+  d.n_img = 1;
+  d.H = 1;
+  d.W = M;
+  d.C = K;
+  d.lda = K;
+  d.B = static_cast<const __half*>(b16);
+  d.rows_b = N;
+  d.N = N;
+  d.conv = CONV_1x1;
+  d.epi = EPI_F32;
+  d.block_n = block_n;
+  d.e.out = out32;
+  d.e.ldo = N;
+  d.e.bias = bias;
+  d.e.alpha = 1.f;
+  if (getenv("RGM_DEBUG_SKIP_STORE")) d.e.act = 99;  // development knob (see gemm_tc.cuh)
+  std::string err;
+  if (launch_gemm(d, static_cast<cudaStream_t>(stream), &err) != cudaSuccess) return set_error(err);
+  return 0;
+}
+
+int rgm_conv_f16(const void* x16, const void* w16_packed, const float* bias, const void* resid16, void* out16,
+                 int n_img, int H, int W, int Cin, int Cout, int kind, int block_n, float* gn_part, void* stream) {
+  if (rgm_check_device()) return -1;
+  GemmDesc d;
+  d.A = static_cast<const __half*>(x16);
+  d.n_img = n_img;
+  d.H = H;
+  d.W = W;
+  d.C = Cin;
+  d.lda = Cin;
+  d.B = static_cast<const __half*>(w16_packed);
+  d.N = Cout;
+  d.rows_b = (kind == CONV_UP2 ? 4 : 1) * Cout;
+  d.conv = kind;
+  d.epi = EPI_F16;
+  d.block_n = block_n;
+  d.e.out = out16;
+  d.e.ldo = Cout;
+  d.e.bias = bias;
+  d.e.alpha = 1.f;
+  d.e.resid = static_cast<const __half*>(resid16);
+  d.e.ldr = Cout;
+  d.e.gn_part = gn_part;
+  if (kind == CONV_UP2) {
+    d.e.up2 = 1;
+    d.e.upH = H;
+    d.e.upW = W;
+  }
+  std::string err;
+  if (launch_gemm(d, static_cast<cudaStream_t>(stream), &err) != cudaSuccess) return set_error(err);
+  return 0;
+}
+
+int rgm_pack_conv_weight(const float* w32, void* w16_packed, int Cout, int Cin, int cout_pad, int cin_pad, int kind,
+                         void* stream) {
+  if (rgm_check_device()) return -1;
+  if (kind < 0 || kind > 2 || cin_pad < Cin || cout_pad < Cout) return set_error("rgm_pack_conv_weight: bad arguments");
+  pack_conv_weight_kernel<<<296, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      w32, static_cast<__half*>(w16_packed), Cout, Cin, cout_pad, cin_pad, kind);
+  g_aux_launches++;
+  return check_cuda(cudaGetLastError(), "rgm_pack_conv_weight");
+}
+
+}  // extern "C"

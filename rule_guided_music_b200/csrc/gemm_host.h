@@ -1,0 +1,40 @@
+// Host-side description of one implicit-GEMM launch (see gemm_tc.cuh).
+#pragma once
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+
+#include <string>
+
+#include "gemm_tc.cuh"
+
+namespace rgm {
+
+enum ConvKind : int {
+  CONV_1x1 = 0,   // also: plain linear layer
+  CONV_3x3 = 1,   // 9 taps, zero padding 1
+  CONV_UP2 = 2,   // nearest-2x upsample followed by 3x3 conv, run as 4 output-parity 2x2 sub-convs
+};
+
+struct GemmDesc {
+  // A operand: fp16 [n_img, H, W, C] with pixel stride lda (elements, >= C, multiple of 8)
+  const __half* A = nullptr;
+  int n_img = 1, H = 1, W = 1, C = 0, lda = 0;
+  // B operand: fp16 [b_batch][rows_b][K]; K = taps * C; rows_b = num_par * N (N padded to the N tile)
+  const __half* B = nullptr;
+  int rows_b = 0, b_batch = 1;
+  int N = 0;          // output columns (multiple of the N tile)
+  int conv = CONV_1x1;
+  int epi = EPI_F16;
+  int block_n = 0;    // 0 = choose
+  EpiParams e{};
+};
+
+// Launch on `stream`. Returns cudaSuccess or the failing status; message in *err if given.
+cudaError_t launch_gemm(const GemmDesc& d, cudaStream_t stream, std::string* err = nullptr);
+
+// number of kernels this translation unit has launched since process start (bench.py's gpu_launches claim)
+unsigned long long gemm_launch_count();
+
+int device_sm_count();
+
+}  // namespace rgm

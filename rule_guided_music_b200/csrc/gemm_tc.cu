@@ -1,0 +1,235 @@
+// Host launcher for the tcgen05 implicit-GEMM kernel: builds the TMA tensor maps and picks the tile shape.
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <unordered_map>
+
+#include "gemm_host.h"
+
+namespace rgm {
+
+namespace {
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+PFN_encodeTiled get_encode() {
+  static PFN_encodeTiled fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_encodeTiled>(p);
+  });
+  return fn;
+}
+
+struct MapKey {
+  const void* ptr;
+  unsigned long long d[4];
+  unsigned long long s[3];
+  unsigned box[4];
+  int rank;
+  bool operator==(const MapKey& o) const { return std::memcmp(this, &o, sizeof(MapKey)) == 0; }
+};
+struct MapKeyHash {
+  size_t operator()(const MapKey& k) const {
+    const unsigned char* b = reinterpret_cast<const unsigned char*>(&k);
+    size_t h = 1469598103934665603ull;
+    for (size_t i = 0; i < sizeof(MapKey); ++i) h = (h ^ b[i]) * 1099511628211ull;
+    return h;
+  }
+};
+
+std::mutex g_map_mu;
+std::unordered_map<MapKey, CUtensorMap, MapKeyHash> g_maps;
+
+// fp16 tensor map, 128-byte swizzle, zero fill out of bounds. dims/strides innermost first; strides in bytes
+// for dims 1..rank-1.
+bool make_map(CUtensorMap* out, const void* ptr, int rank, const cuuint64_t* dims, const cuuint64_t* strides,
+              const cuuint32_t* box, std::string* err) {
+  MapKey key;
+  std::memset(&key, 0, sizeof(key));
+  key.ptr = ptr;
+  key.rank = rank;
+  for (int i = 0; i < rank; ++i) {
+    key.d[i] = dims[i];
+    key.box[i] = box[i];
+    if (i) key.s[i - 1] = strides[i - 1];
+  }
+  {
+    std::lock_guard<std::mutex> lk(g_map_mu);
+    auto it = g_maps.find(key);
+    if (it != g_maps.end()) {
+      *out = it->second;
+      return true;
+    }
+  }
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) {
+    if (err) *err = "cuTensorMapEncodeTiled not available from the driver";
+    return false;
+  }
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, rank, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    if (err) {
+      char buf[256];
+      snprintf(buf, sizeof buf, "cuTensorMapEncodeTiled failed (%d): rank %d dims %llu %llu %llu %llu box %u %u %u %u",
+               (int)r, rank, (unsigned long long)dims[0], (unsigned long long)dims[1],
+               (unsigned long long)(rank > 2 ? dims[2] : 0), (unsigned long long)(rank > 3 ? dims[3] : 0), box[0],
+               box[1], rank > 2 ? box[2] : 0, rank > 3 ? box[3] : 0);
+      *err = buf;
+    }
+    return false;
+  }
+  std::lock_guard<std::mutex> lk(g_map_mu);
+  if (g_maps.size() > 4096) g_maps.clear();
+  g_maps.emplace(key, *out);
+  return true;
+}
+
+std::atomic<unsigned long long> g_launches{0};
+
+template <int BN, int EPI>
+cudaError_t launch_inst(const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& p, int grid,
+                        cudaStream_t stream) {
+  static bool attr_set = false;
+  auto kern = gemm_tc_kernel<BN, EPI>;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)GemmCfg<BN>::SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  kern<<<grid, GEMM_THREADS, GemmCfg<BN>::SMEM_BYTES, stream>>>(ma, mb, p);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return cudaGetLastError();
+}
+
+}  // namespace
+
+unsigned long long gemm_launch_count() { return g_launches.load(); }
+
+int device_sm_count() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+cudaError_t launch_gemm(const GemmDesc& d, cudaStream_t stream, std::string* err) {
+  auto fail = [&](const char* m) {
+    if (err) *err = m;
+    return cudaErrorInvalidValue;
+  };
+  if (d.C % GEMM_BLOCK_K != 0) return fail("gemm: C must be a multiple of 64");
+  if (d.lda % 8 != 0 || d.lda < d.C) return fail("gemm: lda must be >= C and a multiple of 8");
+  if ((reinterpret_cast<uintptr_t>(d.A) & 15) || (reinterpret_cast<uintptr_t>(d.B) & 15))
+    return fail("gemm: operands must be 16-byte aligned");
+
+  GemmParams p;
+  std::memset(&p, 0, sizeof(p));
+  const int bw = d.W < 128 ? d.W : 128;
+  if (128 % bw != 0) return fail("gemm: W must divide 128 or be >= 128");
+  const int bh = 128 / bw;
+  if (bh > 1 && d.H % bh != 0) return fail("gemm: H not a multiple of the tile height");
+  if (d.H > 1 && d.W > 128) return fail("gemm: images wider than 128 pixels are not supported");
+  if (d.n_img > 1 && d.H == 1 && d.W % 128 != 0) return fail("gemm: batched rows must be a multiple of 128");
+  p.bw = bw;
+  p.bh = bh;
+  p.tiles_per_row = (d.W + bw - 1) / bw;
+  p.tiles_per_img = p.tiles_per_row * (d.H / bh > 0 ? d.H / bh : 1);
+  p.M = d.n_img * d.H * d.W;
+  p.N = d.N;
+  p.num_m_tiles = d.n_img * p.tiles_per_img;
+  p.kb_per_tap = d.C / GEMM_BLOCK_K;
+  p.b_batched = d.b_batch > 1 ? 1 : 0;
+  p.num_par = 1;
+  if (d.conv == CONV_1x1) {
+    p.num_taps = 1;
+  } else if (d.conv == CONV_3x3) {
+    p.num_taps = 9;
+    for (int t = 0; t < 9; ++t) {
+      p.tap_dy[0][t] = (signed char)(t / 3 - 1);
+      p.tap_dx[0][t] = (signed char)(t % 3 - 1);
+    }
+  } else if (d.conv == CONV_UP2) {
+    p.num_taps = 4;
+    p.num_par = 4;
+    for (int par = 0; par < 4; ++par)
+      for (int t = 0; t < 4; ++t) {
+        p.tap_dy[par][t] = (signed char)((t >> 1) + (par >> 1) - 1);
+        p.tap_dx[par][t] = (signed char)((t & 1) + (par & 1) - 1);
+      }
+  } else {
+    return fail("gemm: unknown conv kind");
+  }
+  p.epi = d.e;
+
+  int bn = d.block_n;
+  if (bn == 0) {
+    const long long tiles128 = (long long)p.num_m_tiles * p.num_par * (d.N / 128 > 0 ? d.N / 128 : 1);
+    if (d.N % 256 == 0 && tiles128 / 2 >= 2LL * device_sm_count()) bn = 256;
+    else if (d.N % 128 == 0) bn = 128;
+    else bn = 32;
+  }
+  if (d.N % bn != 0) return fail("gemm: N must be a multiple of the N tile");
+  if (d.rows_b < p.num_par * d.N) return fail("gemm: B has fewer rows than num_par * N");
+  p.num_n_tiles = d.N / bn;
+
+  CUtensorMap ma, mb;
+  {
+    cuuint64_t dims[4] = {(cuuint64_t)d.C, (cuuint64_t)d.W, (cuuint64_t)d.H, (cuuint64_t)d.n_img};
+    cuuint64_t strides[3] = {(cuuint64_t)d.lda * 2, (cuuint64_t)d.W * d.lda * 2, (cuuint64_t)d.H * d.W * d.lda * 2};
+    cuuint32_t box[4] = {GEMM_BLOCK_K, (cuuint32_t)bw, (cuuint32_t)bh, 1};
+    if (!make_map(&ma, d.A, 4, dims, strides, box, err)) return cudaErrorInvalidValue;
+  }
+  {
+    const long long K = (long long)p.num_taps * d.C;
+    cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)d.rows_b, (cuuint64_t)d.b_batch};
+    cuuint64_t strides[2] = {(cuuint64_t)K * 2, (cuuint64_t)K * d.rows_b * 2};
+    cuuint32_t box[3] = {GEMM_BLOCK_K, (cuuint32_t)bn, 1};
+    if (!make_map(&mb, d.B, 3, dims, strides, box, err)) return cudaErrorInvalidValue;
+  }
+
+  const long long total = (long long)p.num_m_tiles * p.num_n_tiles * p.num_par;
+  const int grid = (int)(total < device_sm_count() ? total : device_sm_count());
+  if (grid <= 0) return cudaSuccess;
+
+  cudaError_t st = cudaErrorInvalidValue;
+#define RGM_CASE(BN, EPI)                                              \
+  if (bn == BN && d.epi == EPI) {                                      \
+    st = launch_inst<BN, EPI>(ma, mb, p, grid, stream);                \
+    goto done;                                                         \
+  }
+  RGM_CASE(256, EPI_F16)
+  RGM_CASE(128, EPI_F16)
+  RGM_CASE(32, EPI_F16)
+  RGM_CASE(256, EPI_F32)
+  RGM_CASE(128, EPI_F32)
+  RGM_CASE(32, EPI_F32)
+  RGM_CASE(256, EPI_GATE_RESID)
+  RGM_CASE(128, EPI_GATE_RESID)
+  RGM_CASE(256, EPI_QKV_ROPE)
+  RGM_CASE(128, EPI_QKV_ROPE)
+  RGM_CASE(32, EPI_UNPATCH)
+  RGM_CASE(32, EPI_ROLL)
+#undef RGM_CASE
+  return fail("gemm: no kernel instance for this (N tile, epilogue)");
+done:
+  if (st != cudaSuccess && err) *err = std::string("gemm launch: ") + cudaGetErrorString(st);
+  return st;
+}
+
+}  // namespace rgm

@@ -1,0 +1,107 @@
+"""Parity of the tcgen05 implicit-GEMM kernel (linear / conv3x3 / conv1x1 / upsample-conv) against torch fp32 on the
+same fp16-rounded operands.  Tolerances: the kernel accumulates in fp32 like the reference math, so the only
+differences are summation order (and, for the upsample conv, pre-summed fp16 weights): 2e-3 * max|ref| absolute."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from rule_guided_music_b200 import _lib
+
+pytestmark = pytest.mark.gpu
+
+
+def _gemm(a16, b16, bias, block_n=0):
+    M, K = a16.shape
+    N = b16.shape[0]
+    out = torch.empty(M, N, device=a16.device, dtype=torch.float32)
+    _lib.call("rgm_gemm_f16", _lib.ptr(a16), _lib.ptr(b16), _lib.ptr(bias), _lib.ptr(out), M, N, K, block_n,
+              _lib.stream_ptr())
+    return out
+
+
+@pytest.mark.parametrize("M,N,K,bn", [
+    (256, 128, 64, 128),
+    (128, 128, 256, 128),
+    (1000, 384, 1152, 128),
+    (4096, 512, 512, 256),
+    (512, 32, 1152, 32),
+    (300, 256, 4608, 0),
+    (33000, 1152, 1152, 0),
+])
+def test_linear(cuda, M, N, K, bn):
+    g = torch.Generator(device="cpu").manual_seed(M + N + K)
+    a = torch.randn(M, K, generator=g).to(cuda).half()
+    b = (torch.randn(N, K, generator=g) / K ** 0.5).to(cuda).half()
+    bias = torch.randn(N, generator=g).to(cuda)
+    out = _gemm(a, b, bias, bn)
+    ref = a.float() @ b.float().t() + bias
+    torch.cuda.synchronize()
+    err = (out - ref).abs().max().item()
+    assert err <= 2e-3 * ref.abs().max().item(), err
+
+
+def _pack(w, kind, cin_pad=None, cout_pad=None):
+    cout, cin = w.shape[:2]
+    cin_pad = cin_pad or cin
+    cout_pad = cout_pad or cout
+    taps = {0: 1, 1: 9, 2: 4}[kind]
+    npar = 4 if kind == 2 else 1
+    out = torch.empty(npar * cout_pad * taps * cin_pad, device=w.device, dtype=torch.float16)
+    _lib.call("rgm_pack_conv_weight", _lib.ptr(w.contiguous()), _lib.ptr(out), cout, cin, cout_pad, cin_pad, kind,
+              _lib.stream_ptr())
+    return out
+
+
+def _conv(x_nhwc16, wp, bias, cout, kind, resid=None, bn=0, gn_part=None):
+    n, H, W, cin = x_nhwc16.shape
+    s = 2 if kind == 2 else 1
+    out = torch.empty(n, H * s, W * s, cout, device=x_nhwc16.device, dtype=torch.float16)
+    _lib.call("rgm_conv_f16", _lib.ptr(x_nhwc16), _lib.ptr(wp), _lib.ptr(bias), _lib.ptr(resid), _lib.ptr(out), n, H,
+              W, cin, cout, kind, bn, _lib.ptr(gn_part), _lib.stream_ptr())
+    return out
+
+
+@pytest.mark.parametrize("n,H,cin,cout,kind", [
+    (3, 16, 64, 128, 1),
+    (2, 32, 128, 256, 1),
+    (1, 128, 64, 128, 1),
+    (2, 64, 256, 256, 1),
+    (5, 16, 512, 512, 0),
+    (2, 16, 64, 128, 2),
+    (2, 64, 128, 256, 2),
+    (3, 32, 256, 128, 0),
+])
+def test_conv(cuda, n, H, cin, cout, kind):
+    g = torch.Generator(device="cpu").manual_seed(n * 1000 + H + cin + cout + kind)
+    x = torch.randn(n, cin, H, H, generator=g).to(cuda).half()
+    k = 1 if kind == 0 else 3
+    w = (torch.randn(cout, cin, k, k, generator=g) / (cin * k * k) ** 0.5).to(cuda)
+    bias = torch.randn(cout, generator=g).to(cuda)
+    wp = _pack(w, kind)
+    x_nhwc = x.permute(0, 2, 3, 1).contiguous()
+    out = _conv(x_nhwc, wp, bias, cout, kind).float().permute(0, 3, 1, 2)
+    xin = x.float()
+    if kind == 2:
+        xin = F.interpolate(xin, scale_factor=2.0, mode="nearest")
+    ref = F.conv2d(xin, w.half().float(), bias, padding=k // 2)
+    torch.cuda.synchronize()
+    err = (out - ref).abs().max().item()
+    tol = (4e-3 if kind == 2 else 2e-3) * ref.abs().max().item()
+    assert err <= tol, (err, tol)
+
+
+def test_conv_resid_and_gn_partials(cuda):
+    n, H, cin, cout = 2, 32, 128, 128
+    g = torch.Generator(device="cpu").manual_seed(7)
+    x = torch.randn(n, H, H, cin, generator=g).to(cuda).half()
+    w = (torch.randn(cout, cin, 3, 3, generator=g) / (cin * 9) ** 0.5).to(cuda)
+    bias = torch.randn(cout, generator=g).to(cuda)
+    resid = torch.randn(n, H, H, cout, generator=g).to(cuda).half()
+    part = torch.zeros(n * H * H // 32, cout // 4, 2, device=cuda)
+    out = _conv(x, _pack(w, 1), bias, cout, 1, resid=resid, gn_part=part)
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.half().float(), bias, padding=1).permute(0, 2, 3, 1) + resid.float()
+    torch.cuda.synchronize()
+    assert (out.float() - ref).abs().max().item() <= 4e-3 * ref.abs().max().item()
+    o = out.float().reshape(n * H * H // 32, 32, cout // 4, 4)
+    assert torch.allclose(part[..., 0], o.sum(dim=(1, 3)), rtol=1e-4, atol=1e-2)
+    assert torch.allclose(part[..., 1], (o * o).sum(dim=(1, 3)), rtol=1e-4, atol=1e-2)

@@ -1,0 +1,167 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference (/root/reference) on CPU.
+
+Run in the build container only (the reference does not travel to the GPU box):
+    python tests/golden/make_golden.py
+The reference needs nine packages that are not installed here; `ref_shims/` holds import stand-ins (no-ops for
+matplotlib/mpi4py/blobfile/omegaconf/pytorch_lightning/mido/music21, and behavioural restatements of timm.Mlp and
+rotary_embedding_torch.RotaryEmbedding -- see oracle/__init__.py for what that means for pinning).
+Inputs are regenerated from seeds by the tests (tests/golden_inputs.py), so only reference OUTPUTS are stored.
+"""
+import os
+import sys
+from functools import partial
+from types import SimpleNamespace
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(HERE, "ref_shims"))
+sys.path.insert(0, os.environ.get("RGM_REFERENCE", "/root/reference"))
+
+import guided_diffusion.gaussian_diffusion as gd  # noqa: E402
+import guided_diffusion.dit as rdit  # noqa: E402
+from guided_diffusion import respace as rrespace  # noqa: E402
+from guided_diffusion.condition_functions import model_fn  # noqa: E402
+from guided_diffusion.script_util import create_diffusion  # noqa: E402
+from music_rule_guidance.rule_maps import FUNC_DICT, LOSS_DICT  # noqa: E402
+from taming.modules.diffusionmodules.model import Decoder  # noqa: E402
+
+from oracle import weights as ow  # noqa: E402
+from tests import golden_inputs as gi  # noqa: E402
+
+torch.set_grad_enabled(False)
+
+
+def save(name, **arrays):
+    path = os.path.join(HERE, name + ".npz")
+    np.savez_compressed(path, **{k: np.asarray(v) for k, v in arrays.items()})
+    print(f"wrote {path} ({os.path.getsize(path) / 1024:.1f} KiB)")
+
+
+# ---------------------------------------------------------------------------------------------------------------
+def golden_schedule():
+    out = {}
+    d = create_diffusion(diffusion_steps=1000, noise_schedule="linear", timestep_respacing="")
+    for k in gi.SCHEDULE_KEYS:
+        out["full_" + k] = getattr(d, k)
+    out["full_fixed_large_variance"] = np.append(d.posterior_variance[1], d.betas[1:])
+    for resp in ("256", "ddim50", "4", "ddim25", "10,15,20"):
+        s = create_diffusion(diffusion_steps=1000, noise_schedule="linear", timestep_respacing=resp)
+        tag = resp.replace(",", "_")
+        out[f"resp_{tag}_betas"] = s.betas
+        out[f"resp_{tag}_map"] = np.array(s.timestep_map)
+    try:
+        rrespace.space_timesteps(1000, "ddim256")
+        out["ddim256_raises"] = 0
+    except ValueError:
+        out["ddim256_raises"] = 1
+    c = create_diffusion(diffusion_steps=100, noise_schedule="cosine", timestep_respacing="")
+    out["cosine100_betas"] = c.betas
+    save("schedule", **out)
+
+
+def golden_rules():
+    out = {}
+    for case, roll in gi.rule_rolls().items():
+        for name in gi.RULE_NAMES:
+            out[f"{case}__{name}"] = FUNC_DICT[name](roll.clone()).numpy()
+    # order dependence: pitch_hist evaluated after note_density on the SAME tensor (in-place threshold)
+    r = gi.rule_rolls()["order"]
+    FUNC_DICT["note_density"](r)
+    out["order__pitch_hist_after_nd"] = FUNC_DICT["pitch_hist"](r).numpy()
+    out["order__roll_after"] = r[:, 0, 55:70, :16].numpy()
+    # losses
+    g, t = gi.loss_pairs()
+    out["loss_mse"] = LOSS_DICT["pitch_hist"](g, t).numpy()
+    out["loss_zero_one"] = LOSS_DICT["note_density_class"](g.round().long(), t.round().long()).numpy()
+    save("rules", **out)
+
+
+def build_ref_dit(cfg):
+    sd = ow.make_dit_state_dict(**cfg["weights"])
+    if cfg.get("preset"):
+        model = rdit.DiT_models[cfg["preset"]](input_size=cfg["input_size"], in_channels=4,
+                                               num_classes=cfg["weights"].get("num_classes", 3),
+                                               learn_sigma=cfg["weights"].get("learn_sigma", False))
+    else:
+        w = cfg["weights"]
+        model = rdit.DiTRotary(input_size=cfg["input_size"], patch_size=w["patch"], in_channels=4,
+                               hidden_size=w["hidden"], depth=w["depth"], num_heads=w["heads"],
+                               num_classes=w.get("num_classes", 3), learn_sigma=w.get("learn_sigma", False))
+    missing, unexpected = model.load_state_dict(sd, strict=True), None
+    del missing, unexpected
+    return model.eval(), sd
+
+
+def golden_dit():
+    out = {}
+    for tag, cfg in gi.DIT_CASES.items():
+        model, _ = build_ref_dit(cfg)
+        x, t, y = gi.dit_inputs(cfg)
+        out[tag] = model(x, t, y).numpy()
+        if cfg.get("half_tile"):
+            xh = x[:, :, :64].contiguous()
+            out[tag + "__half"] = model(xh, t, y).numpy()
+        del model
+    save("dit", **out)
+
+
+def build_ref_vae():
+    sd = ow.make_vae_state_dict(seed=gi.VAE_SEED)
+    dec = Decoder(**ow.VAE_DDCONFIG)
+    pq = torch.nn.Conv2d(4, 4, 1)
+    dec.load_state_dict({k[len("decoder."):]: v for k, v in sd.items() if k.startswith("decoder.")}, strict=True)
+    pq.load_state_dict({k[len("post_quant_conv."):]: v for k, v in sd.items() if k.startswith("post_quant_conv.")},
+                       strict=True)
+
+    class Embed:  # what AutoencoderKL.decode does (klvae_pedal.py:80-85)
+        @staticmethod
+        def decode(z):
+            return dec(pq(z))
+
+    return Embed
+
+
+def golden_vae():
+    embed = build_ref_vae()
+    z = gi.vae_tiles()
+    out = {"tiles": embed.decode(z).numpy().astype(np.float32)}
+    lat = gi.vae_latents()
+    roll = gd._decode(lat, embed, scale_factor=gi.SCALE_FACTOR)
+    out["decode_latents_sub4"] = roll[:, :, ::4, ::4].numpy()
+    out["decode_latents_ch0_stats"] = np.array([roll[:, 0].mean().item(), roll[:, 0].std().item()])
+    save("vae", **out)
+
+
+def golden_sampler():
+    """Short guided trajectories through the reference's own loops (seeded torch CPU RNG = shared noise stream)."""
+    embed = build_ref_vae()
+    out = {}
+    for tag, cfg in gi.SAMPLER_CASES.items():
+        model, _ = build_ref_dit(gi.DIT_CASES[cfg["dit"]])
+        diffusion = create_diffusion(diffusion_steps=1000, noise_schedule="linear",
+                                     timestep_respacing=cfg["respacing"])
+        fn = partial(model_fn, model=model, num_classes=3, class_cond=True, cfg=False, w=0.0)
+        kwargs = gi.sampler_model_kwargs(cfg)
+        guidance = SimpleNamespace(**cfg["guidance"]) if cfg.get("guidance") else None
+        loop = diffusion.ddim_sample_loop_progressive if cfg["ddim"] else diffusion.p_sample_loop_progressive
+        extra = {"eta": cfg["eta"]} if cfg["ddim"] else {}
+        diffusion.t_end = cfg.get("t_end", 0)
+        torch.manual_seed(cfg["seed"])
+        steps = []
+        for o in loop(fn, cfg["shape"], model_kwargs=kwargs, device="cpu", embed_model=embed if cfg["scg"] else None,
+                      scale_factor=gi.SCALE_FACTOR, guidance_kwargs=guidance,
+                      scg_kwargs=dict(cfg["scg"]) if cfg["scg"] else None, t_end=cfg.get("t_end", 0), **extra):
+            steps.append(o["sample"].numpy().copy())
+        out[tag] = np.stack(steps)
+        del model
+    save("sampler", **out)
+
+
+if __name__ == "__main__":
+    which = sys.argv[1:] or ["schedule", "rules", "dit", "vae", "sampler"]
+    for w in which:
+        globals()["golden_" + w]()

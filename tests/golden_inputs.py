@@ -1,0 +1,143 @@
+"""Seeded inputs shared by the golden-vector generator (tests/golden/make_golden.py, runs the unmodified reference),
+the CPU oracle tests and the GPU parity tests.  Only reference OUTPUTS are stored under tests/golden/; inputs are
+regenerated here from seeds with torch's CPU generator, which is identical in the build container and on the GPU box.
+"""
+import torch
+
+SCALE_FACTOR = 1.2465  # reference README.md:59
+VAE_SEED = 1
+
+SCHEDULE_KEYS = [
+    "betas", "alphas_cumprod", "alphas_cumprod_prev", "alphas_cumprod_next", "sqrt_alphas_cumprod",
+    "sqrt_one_minus_alphas_cumprod", "log_one_minus_alphas_cumprod", "sqrt_recip_alphas_cumprod",
+    "sqrt_recipm1_alphas_cumprod", "posterior_variance", "posterior_log_variance_clipped", "posterior_mean_coef1",
+    "posterior_mean_coef2",
+]
+
+RULE_NAMES = ["pitch_hist", "note_density", "note_density_hr_1", "note_density_hr_2", "note_density_class",
+              "note_density_pixel"]
+
+# ---------------------------------------------------------------------------------------------------------------
+# DiT
+# ---------------------------------------------------------------------------------------------------------------
+DIT_CASES = {
+    # small model with the XL head geometry (head_dim 72, rotary 36) so every kernel path is exercised quickly
+    "small": dict(preset=None, input_size=[128, 16], batch=3, half_tile=True,
+                  weights=dict(seed=11, depth=2, hidden=576, patch=8, heads=8, num_classes=3)),
+    # head_dim 64 (DiTRotary_B geometry), patch 16
+    "small_hd64": dict(preset=None, input_size=[128, 16], batch=2, half_tile=False,
+                       weights=dict(seed=12, depth=2, hidden=256, patch=16, heads=4, num_classes=3)),
+    # the flagship: DiTRotary_XL_8 (depth 28, hidden 1152, 16 heads), reference dit.py:902
+    "xl8": dict(preset="DiTRotary_XL_8", input_size=[128, 16], batch=2, half_tile=True,
+                weights=dict(seed=0, depth=28, hidden=1152, patch=8, heads=16, num_classes=3)),
+}
+
+
+def dit_inputs(cfg):
+    g = torch.Generator(device="cpu").manual_seed(1000 + cfg["weights"]["seed"])
+    B = cfg["batch"]
+    H, W = cfg["input_size"]
+    x = torch.randn(B, 4, H, W, generator=g)
+    t = torch.randint(0, 1000, (B,), generator=g)
+    y = torch.randint(0, cfg["weights"]["num_classes"], (B,), generator=g)
+    return x, t, y
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# rules
+# ---------------------------------------------------------------------------------------------------------------
+def rule_rolls():
+    """Hand-built and random piano rolls [B,3,128,1024] in [-1,1]."""
+    rolls = {}
+    pr = -torch.ones(2, 3, 128, 1024)
+    pr[0, 0, 60, 0:128] = 1
+    pr[1, 0, 61, 100:300] = 0.5
+    pr[1, 0, 73, 100:300] = 0.5
+    pr[1, 0, 10, :] = 1
+    pr[1, 0, 110, :] = 1
+    pr[1, 0, 64, 512] = -0.95
+    pr[1, 0, 65, 513] = -0.951
+    rolls["kat"] = pr
+    o = -torch.ones(2, 3, 128, 1024)
+    o[0, 0, 60, :] = -1.2
+    o[0, 0, 62, :10] = 1
+    o[1, 0, 40, 5:900] = 0.3
+    rolls["order"] = o
+    g = torch.Generator(device="cpu").manual_seed(77)
+    # sparse random notes: values near the -0.95 threshold, out-of-range pitches, values beyond [-1, 1]
+    r = -torch.ones(4, 3, 128, 1024)
+    mask = torch.rand(4, 128, 1024, generator=g) < 0.03
+    vals = torch.rand(4, 128, 1024, generator=g) * 2.4 - 1.2
+    r[:, 0] = torch.where(mask, vals, r[:, 0])
+    near = torch.rand(4, 128, 1024, generator=g) < 0.01
+    r[:, 0] = torch.where(near, -0.95 + (torch.rand(4, 128, 1024, generator=g) - 0.5) * 1e-3, r[:, 0])
+    rolls["random"] = r
+    one = -torch.ones(1, 3, 128, 1024)
+    one[0, 0, 50:55, 200:600] = 0.7
+    rolls["single"] = one  # B == 1: the reference squeezes the batch dimension
+    return rolls
+
+
+def loss_pairs():
+    g = torch.Generator(device="cpu").manual_seed(5)
+    return torch.rand(6, 16, generator=g) * 8, torch.rand(6, 16, generator=g) * 8
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# VAE
+# ---------------------------------------------------------------------------------------------------------------
+def vae_tiles(n=2):
+    g = torch.Generator(device="cpu").manual_seed(21)
+    return torch.randn(n, 4, 16, 16, generator=g)
+
+
+def vae_latents(B=2, H=32):
+    g = torch.Generator(device="cpu").manual_seed(22)
+    return torch.randn(B, 4, H, 16, generator=g) * SCALE_FACTOR
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# sampler trajectories (teacher data: every intermediate x_t of a short loop through the reference)
+# ---------------------------------------------------------------------------------------------------------------
+_GUIDE_ON = dict(schedule=False, t_start=750, t_end=0, interval=1, method="scg", step_size=1.0, nn=False)
+_GUIDE_SCHED = dict(schedule=True, t_start=750, t_end=0, interval=2, method="scg", step_size=1.0, nn=False)
+
+SAMPLER_CASES = {
+    # plain ancestral sampling, 4 respaced steps, no guidance
+    "ddpm_plain": dict(dit="small", respacing="4", ddim=False, shape=(2, 4, 128, 16), seed=3, scg=None,
+                       guidance=None),
+    # DDIM eta=0 / eta=1 without guidance
+    "ddim_plain": dict(dit="small", respacing="ddim4", ddim=True, eta=0.0, shape=(2, 4, 128, 16), seed=4, scg=None,
+                       guidance=None),
+    # DDIM(eta=1) + SCG, pitch histogram, N=3 (config-3 shape in miniature); H=32 latents = 2 VAE tiles
+    "ddim_scg_pitch": dict(dit="small", respacing="4", ddim=True, eta=1.0, shape=(2, 4, 32, 16), seed=5,
+                           scg=dict(num_samples=3, pitch_hist=1.0), guidance=_GUIDE_ON, rules=["pitch_hist"]),
+    # DDPM + SCG with two rules (order dependent in-place masking) and a scheduled guidance window
+    "ddpm_scg_two": dict(dit="small", respacing="6", ddim=False, shape=(2, 4, 32, 16), seed=6,
+                         scg=dict(num_samples=2, note_density=0.5, pitch_hist=2.0), guidance=_GUIDE_SCHED,
+                         rules=["pitch_hist", "note_density"]),
+}
+
+
+def rule_targets(B, L, names):
+    """Targets in the layout sample_rule.py builds (scripts/sample_rule.py:139-198); L = roll length."""
+    nwin = L // 128
+    out = {}
+    for n in names:
+        if n == "pitch_hist":
+            out[n] = torch.tensor([0.5, 0, 0, 0, 0.25, 0, 0, 0.25, 0, 0, 0, 0]).repeat(B, 1)
+        elif n.startswith("note_density"):
+            v = torch.tensor([1., 1, 2, 3, 3, 2, 1, 1])[:nwin] if nwin <= 8 else torch.ones(nwin)
+            h = torch.tensor([5., 5, 10, 15, 15, 10, 5, 5])[:nwin] / 5 if nwin <= 8 else torch.ones(nwin)
+            out[n] = torch.cat([v, h]).repeat(B, 1)
+        else:
+            raise KeyError(n)
+    return out
+
+
+def sampler_model_kwargs(cfg):
+    B, _, H, _ = cfg["shape"]
+    kw = {"y": torch.ones(B, dtype=torch.long)}
+    if cfg.get("rules"):
+        kw["rule"] = rule_targets(B, H * 8, cfg["rules"])
+    return kw

@@ -2,15 +2,18 @@
  * rgm_b200 -- C ABI of the B200-native (sm_100a) rule-guided sampling hot path.
  *
  * The reference (yjhuangcd/rule-guided-music) is pure Python/PyTorch and has no FFI of its own; its drop-in boundary
- * for this path is four Python callables.  Every entry point below names the reference
- * callable(s) it replaces.  The Python mirror of the reference API (rule_guided_music_b200/) binds these with ctypes;
+ * for this path is four Python callables: the denoiser `model(x, t, **kw)`, the latent decoder
+ * `embed_model.decode(z)`, the rule programs `FUNC_DICT[name](roll)` / `LOSS_DICT[name]`, and the sampler methods that
+ * call them.  Every entry point below names the reference callable(s) it replaces (file:line under the reference
+ * repository).  The Python mirror of the reference API (rule_guided_music_b200/) binds these with ctypes;
  * INTEGRATION.md shows the stub a maintainer of the reference would add.
  *
  * Conventions
  *   - plain pointers and sizes only; all pointers are DEVICE pointers unless the name ends in _host
- *   - all work is enqueued on the caller's stream (a cudaStream_t passed as void*), nothing synchronises
+ *   - all work is enqueued on the caller's stream (a cudaStream_t passed as void*); compute calls do not synchronise
+ *     (a handle's workspace grows on first use of a larger batch, which does synchronise once)
  *   - return 0 on success, negative on error; rgm_last_error() returns the message for the calling thread
- *   - handles own their packed weights and workspace; the workspace grows on first use of a larger batch
+ *   - handles own their packed weights and workspace; one handle is used by one host thread at a time
  *   - there is no CPU fallback: without an sm_100 device every compute entry point fails with an error
  */
 #ifndef RGM_B200_H_
@@ -30,6 +33,65 @@ unsigned long long rgm_launch_count(void);
 /* 0 when the current device is sm_100 (B200); negative with an error message otherwise */
 int rgm_check_device(void);
 
+/* ---- denoiser: DiTRotary.forward (guided_diffusion/dit.py:538-634; registry DiT_models dit.py:969-983) -------- */
+typedef struct rgm_dit rgm_dit;
+/* DiTRotary.__init__ (dit.py:545-576): label_rows = num_classes + 1 (LabelEmbedder table, dit.py:79-80) or 0 when the
+ * model has no label embedder; latent_w = input_size[1] (16); mlp_hidden = int(hidden * mlp_ratio) */
+int rgm_dit_create(rgm_dit** out, int depth, int hidden, int heads, int patch, int in_channels, int out_channels,
+                   int label_rows, int latent_w, int mlp_hidden);
+int rgm_dit_destroy(rgm_dit* h);
+/* model.load_state_dict(sd, strict=False) (scripts/sample_rule.py:71-73), one tensor per call: `key` is the reference
+ * state-dict key, `src` the fp32 tensor on the device.  Returns 0 = stored (converted to the kernel layout),
+ * 1 = key not part of this path (ignored), negative = error (element count mismatch).
+ * Extra key "__timestep_freqs": the 128 sinusoid frequencies of TimestepEmbedder.timestep_embedding (dit.py:57-59). */
+int rgm_dit_load(rgm_dit* h, const char* key, const float* src, long long numel, void* stream);
+/* model(x, t, y) (dit.py:618-634): x f32 [B, C, H, latent_w]; t f32 [B] (already mapped / rescaled by the caller,
+ * respace.py:123-128); y int64 [B] label rows or NULL (dit.py:627-629); out f32 [B, C_out, H, latent_w].
+ * H * latent_w / patch must be 128 or 256 tokens. */
+int rgm_dit_forward(rgm_dit* h, const float* x, const float* t, const long long* y, float* out, int B, int H,
+                    void* stream);
+
+/* ---- latent decoder: AutoencoderKL.decode (taming/models/klvae_pedal.py:80-85) -------------------------------- */
+typedef struct rgm_vae rgm_vae;
+/* Decoder.__init__ (taming/modules/diffusionmodules/model.py:436-504) with attn_resolutions = [] (mid attention only) */
+int rgm_vae_create(rgm_vae** out, int ch, const int* ch_mult_host, int n_levels, int num_res_blocks, int z_channels,
+                   int out_ch);
+int rgm_vae_destroy(rgm_vae* h);
+/* AutoencoderKL.init_from_ckpt (klvae_pedal.py:50-59), one tensor per call; keys "post_quant_conv.*", "decoder.*".
+ * Same return convention as rgm_dit_load. */
+int rgm_vae_load(rgm_vae* h, const char* key, const float* src, long long numel, void* stream);
+/* _decode(pred_zstart, embed_model, scale_factor) (guided_diffusion/gaussian_diffusion.py:1347-1358):
+ * lat f32 [n_cand, 4, Hlat, 16] -> roll f32 [n_cand, roll_ch, 128, 8*Hlat], roll_ch in [1, out_ch] (the rules read
+ * channel 0 only, music_rules.py:31,56).  embed_model.decode(z [n,4,16,16]) is the case Hlat = 16, scale_factor = 1
+ * with z transposed to [n,4,time,pitch]. */
+int rgm_vae_decode_latents(rgm_vae* h, const float* lat, float scale_factor, float* roll, int n_cand, int Hlat,
+                           int roll_ch, void* stream);
+
+/* ---- rule programs (music_rule_guidance/music_rules.py, rule_maps.py) ----------------------------------------- */
+/* FUNC_DICT["pitch_hist"] = total_pitch_class_histogram (music_rules.py:29-43): roll f32 [n, ch, 128, L] (channel 0
+ * is read AND piano-masked in place, music_rules.py:23-26) -> hist f32 [n, 12] */
+int rgm_rule_pitch_hist(float* roll, float* hist, int n, int ch, int L, void* stream);
+/* FUNC_DICT["note_density" | "note_density_hr_*" | "note_density_pixel"] = note_density(interval, horizontal_scale)
+ * (music_rules.py:46-83; quantize_factor = 1): out f32 [n, 2*L/interval]; channel 0 is thresholded in place */
+int rgm_rule_note_density(float* roll, float* out, int n, int ch, int L, int interval, float horizontal_scale,
+                          void* stream);
+/* scg_sample's per-rule update `total_log_prob += -LOSS_DICT[rule](gen, target.repeat(N,1)) * weight`
+ * (gaussian_diffusion.py:532-538): gen f32 [n, K], target f32 [B, K] (row i uses target i % B), total f32 [n];
+ * kind 0 = mse_loss_mean (rule_maps.py:17-18), 1 = zero_one_loss_mean (rule_maps.py:21-22) */
+int rgm_rule_loss_accum(const float* gen, const float* target, float* total, int n, int B, int K, int kind,
+                        float weight, void* stream);
+
+/* ---- stochastic control guidance (guided_diffusion/gaussian_diffusion.py:491-554) ------------------------------ */
+/* :510-514  cand[n, b, :] = mean[b, :] + g[b] * noise[n, b, :]   (elems = C*H*W per sample) */
+int rgm_scg_fanout(const float* mean, const float* g, const float* noise, float* cand, int N, int B, long long elems,
+                   void* stream);
+/* :359-364  x0 = a[b]*x - c[b]*eps (a = sqrt_recip_alphas_cumprod[t], c = sqrt_recipm1_alphas_cumprod[t]); clamp: +-1 */
+int rgm_x0_from_eps(const float* x, const float* eps, const float* a, const float* c, float* x0, int B,
+                    long long elems, int clamp, void* stream);
+/* :539-554  max_ind = total.view(N, B).argmax(0) (first maximal index); out[b] = cand[max_ind[b], b]; idx int64 [B] */
+int rgm_scg_select(const float* total, const float* cand, float* out, long long* idx, int N, int B, long long elems,
+                   void* stream);
+
 /* ---- building blocks (exposed for the parity tests) ---------------------------------------------------------- */
 /* out32[M,N] = A16[M,K] . B16[N,K]^T + bias[N]      (torch.nn.functional.linear; reference dit.py:256,286,324-326)
  * block_n: 0 = choose, else 32 / 128 / 256 */
@@ -44,6 +106,10 @@ int rgm_conv_f16(const void* x16, const void* w16_packed, const float* bias, con
  * cout_pad >= Cout. Output size: kind 0: cout_pad*cin_pad; kind 1: cout_pad*9*cin_pad; kind 2: 4*cout_pad*4*cin_pad */
 int rgm_pack_conv_weight(const float* w32, void* w16_packed, int Cout, int Cin, int cout_pad, int cin_pad, int kind,
                          void* stream);
+/* softmax(q k^T * scale) v per (sample, head) (dit.py:274-277): q,k fp16 [B,heads,T,dh], vt fp16 [B,heads,dh,T],
+ * out fp16 [B*T, heads*dh]; T in {128, 256} */
+int rgm_attention_f16(const void* q16, const void* k16, const void* vt16, void* out16, int B, int heads, int T, int dh,
+                      float scale, void* stream);
 
 #ifdef __cplusplus
 }

@@ -35,11 +35,28 @@ def _declare(lib):
 
 
 # name -> argtypes; every function returns int (0 = ok)
+_HP = ctypes.POINTER(ctypes.c_void_p)
+c_char_p = ctypes.c_char_p
 _SIGNATURES = {
+    "rgm_dit_create": [_HP, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int],
+    "rgm_dit_destroy": [c_void_p],
+    "rgm_dit_load": [c_void_p, c_char_p, c_void_p, c_ll, c_void_p],
+    "rgm_dit_forward": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p],
+    "rgm_vae_create": [_HP, c_int, ctypes.POINTER(c_int), c_int, c_int, c_int, c_int],
+    "rgm_vae_destroy": [c_void_p],
+    "rgm_vae_load": [c_void_p, c_char_p, c_void_p, c_ll, c_void_p],
+    "rgm_vae_decode_latents": [c_void_p, c_void_p, c_float, c_void_p, c_int, c_int, c_int, c_void_p],
+    "rgm_rule_pitch_hist": [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p],
+    "rgm_rule_note_density": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p],
+    "rgm_rule_loss_accum": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p],
+    "rgm_scg_fanout": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_ll, c_void_p],
+    "rgm_x0_from_eps": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_ll, c_int, c_void_p],
+    "rgm_scg_select": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_ll, c_void_p],
     "rgm_gemm_f16": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
     "rgm_conv_f16": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
                      c_int, c_void_p, c_void_p],
     "rgm_pack_conv_weight": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p],
+    "rgm_attention_f16": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p],
 }
 
 

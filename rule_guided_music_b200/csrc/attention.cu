@@ -1,0 +1,301 @@
+// Multi-head self-attention of the DiT block on tcgen05 (reference guided_diffusion/dit.py:263-288, the
+// F.scaled_dot_product_attention branch): out = softmax(q k^T * scale) v per (sample, head), no mask.
+//
+// One persistent CTA per SM walks over (sample, head) pairs.  Per pair the whole K [T, dh] and V^T [dh, T] sit in
+// shared memory (TMA, 128-byte swizzle), S = Q K^T for each 128-query tile is accumulated in TMEM (T <= 256 fp32
+// columns per tile, two tiles = all 512 columns), four softmax warps (one thread per query row = one TMEM lane) read
+// S, write un-normalised P = exp2((s - max) * scale*log2e) as fp16 into a swizzled K-major smem tile, the MMA thread
+// runs O = P V into the TMEM columns S occupied, and the softmax warps scale O by 1/rowsum on the way out.
+// The two query tiles are software-pipelined: the tensor core computes S1 and P0 V while the softmax warps work on
+// tile 0 / tile 1, so the MUFU-bound softmax (128 x T exponentials per tile) overlaps the MMAs.
+#include <atomic>
+#include <mutex>
+#include <unordered_map>
+
+#include "aux_kernels.h"
+#include "ptx.cuh"
+
+namespace rgm {
+
+namespace {
+
+constexpr int ATT_THREADS = 160;  // warp 0: TMA + MMA issue (+ TMEM owner); warps 1..4: softmax / epilogue
+
+struct AttnParams {
+  int n_pairs;   // B * heads
+  int heads, T, dh;
+  int nkb;       // 64-wide k-blocks of the head dimension (1 or 2)
+  int ksteps;    // ceil(dh / 16) MMA K steps for S
+  int npv;       // dh rounded up to 16: N of the P V MMA
+  int n_tiles;   // T / 128
+  float scale_log2e;
+  __half* out;   // [B*T, heads*dh]
+};
+
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+__device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+
+__global__ void __launch_bounds__(ATT_THREADS, 1)
+attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
+                 const __grid_constant__ CUtensorMap map_v, const __grid_constant__ AttnParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int T = p.T;
+  const uint32_t q_bytes = p.nkb * 16384u;           // per query tile: nkb blocks of [128 rows][128 B]
+  const uint32_t k_blk = (uint32_t)T * 128u;         // one k-block of K: [T rows][128 B]
+  const uint32_t v_blk = (uint32_t)p.npv * 128u;     // one 64-token block of V^T: [npv rows][128 B]
+  uint8_t* sQ = smem;                                // two query tiles
+  uint8_t* sK = sQ + 2 * q_bytes;
+  uint8_t* sV = sK + p.nkb * k_blk;
+  uint8_t* sP = sV + (T / 64) * v_blk;               // [T/64 blocks][128 rows][128 B]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + (T / 64) * 16384u);
+  uint64_t* bar_load = bars;        // Q tiles + K + V landed
+  uint64_t* bar_s = bars + 1;       // [2] S tile complete
+  uint64_t* bar_p = bars + 3;       // [2] P tile written (128 arrivals)
+  uint64_t* bar_o = bars + 5;       // [2] O tile complete
+  uint64_t* bar_done = bars + 7;    // epilogue has drained TMEM (128 arrivals)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&map_q);
+    tma_prefetch_desc(&map_k);
+    tma_prefetch_desc(&map_v);
+    mbar_init(bar_load, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&bar_s[i], 1);
+      mbar_init(&bar_p[i], 128);
+      mbar_init(&bar_o[i], 1);
+    }
+    mbar_init(bar_done, 128);
+    fence_barrier_init();
+  }
+  if (warp == 0) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const uint32_t idesc_s = umma_idesc_f16(128, T);
+  const uint32_t idesc_o = umma_idesc_f16(128, p.npv);
+  const uint32_t load_bytes = p.n_tiles * q_bytes + p.nkb * k_blk + (T / 64) * v_blk;
+
+  uint32_t it = 0;
+  for (int pair = blockIdx.x; pair < p.n_pairs; pair += gridDim.x, ++it) {
+    const uint32_t ph = it & 1;
+    if (warp == 0) {
+      if (lane == 0) {
+        // all MMAs of the previous pair have completed (bar_o was waited on by the epilogue, which then arrived on
+        // bar_done), so every smem operand buffer and the TMEM columns are free
+        if (it > 0) mbar_wait(bar_done, ph ^ 1);
+        tc_fence_after();
+        mbar_arrive_expect_tx(bar_load, load_bytes);
+        const int row0 = pair * T;
+        for (int kb = 0; kb < p.nkb; ++kb) {
+          for (int m = 0; m < p.n_tiles; ++m)
+            tma_load_2d(sQ + m * q_bytes + kb * 16384, &map_q, bar_load, kb * 64, row0 + m * 128);
+          for (int j = 0; j < p.n_tiles; ++j)
+            tma_load_2d(sK + kb * k_blk + j * 16384, &map_k, bar_load, kb * 64, row0 + j * 128);
+        }
+        for (int tb = 0; tb < T / 64; ++tb) tma_load_2d(sV + tb * v_blk, &map_v, bar_load, tb * 64, pair * p.dh);
+        mbar_wait(bar_load, ph);
+        tc_fence_after();
+        // S tiles
+        for (int m = 0; m < p.n_tiles; ++m) {
+          for (int ks = 0; ks < p.ksteps; ++ks) {
+            const int kb = ks >> 2, kk = ks & 3;
+            umma_f16(tmem_base + m * 256, umma_desc_sw128(sQ + m * q_bytes + kb * 16384) + 2 * kk,
+                     umma_desc_sw128(sK + kb * k_blk) + 2 * kk, idesc_s, ks != 0);
+          }
+          umma_commit(&bar_s[m]);
+        }
+        // O tiles: P (A operand, K = tokens) x V^T (B operand, [npv rows][tokens])
+        for (int m = 0; m < p.n_tiles; ++m) {
+          mbar_wait(&bar_p[m], ph);
+          tc_fence_after();
+          for (int ks = 0; ks < T / 16; ++ks) {
+            const int tb = ks >> 2, kk = ks & 3;
+            umma_f16(tmem_base + m * 256, umma_desc_sw128(sP + tb * 16384) + 2 * kk,
+                     umma_desc_sw128(sV + tb * v_blk) + 2 * kk, idesc_o, ks != 0);
+          }
+          umma_commit(&bar_o[m]);
+        }
+      }
+      __syncwarp();
+    } else {
+      const int quad = warp & 3;                 // TMEM lane quadrant this warp may touch
+      const int r = quad * 32 + lane;            // query row within the tile
+      float inv_sum[2] = {0.f, 0.f};
+#pragma unroll
+      for (int m = 0; m < 2; ++m) {
+        if (m >= p.n_tiles) break;
+        mbar_wait(&bar_s[m], ph);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + m * 256;
+        float mx = -INFINITY;
+        for (int c = 0; c < T; c += 32) {
+          uint32_t v[32];
+          tmem_ld_32x32(taddr + c, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
+        }
+        // the single P buffer is read by the previous tile's P V MMAs: wait for them before overwriting it
+        if (m > 0) mbar_wait(&bar_o[m - 1], ph);
+        const float mneg = -mx * p.scale_log2e;
+        float sum = 0.f;
+        for (int c = 0; c < T; c += 32) {
+          uint32_t v[32];
+          tmem_ld_32x32(taddr + c, v);
+          tmem_ld_wait();
+          uint4 pk[4];
+          __half2* h2 = reinterpret_cast<__half2*>(pk);
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            const float e0 = ex2(fmaf(__uint_as_float(v[i]), p.scale_log2e, mneg));
+            const float e1 = ex2(fmaf(__uint_as_float(v[i + 1]), p.scale_log2e, mneg));
+            sum += e0 + e1;
+            h2[i >> 1] = __floats2half2_rn(e0, e1);
+          }
+          // columns c..c+31 = 16-byte chunks (c%64)/8 .. +3 of row r in token block c/64, 128-byte swizzle
+          uint8_t* rowp = sP + (c >> 6) * 16384 + r * 128;
+          const int ch0 = (c & 63) >> 3;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(rowp + (((ch0 + j) ^ (r & 7)) << 4)) = pk[j];
+        }
+        inv_sum[m] = 1.0f / sum;
+        tc_fence_before();
+        fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
+        mbar_arrive(&bar_p[m]);
+      }
+      // epilogue: O / rowsum -> out[b*T + row, head*dh + d]
+      const int b = pair / p.heads, head = pair - b * p.heads;
+#pragma unroll
+      for (int m = 0; m < 2; ++m) {
+        if (m >= p.n_tiles) break;
+        mbar_wait(&bar_o[m], ph);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + m * 256;
+        __half* orow = p.out + ((long long)b * T + m * 128 + r) * (p.heads * p.dh) + head * p.dh;
+        for (int c = 0; c < p.npv; c += 16) {
+          uint32_t v[16];
+          tmem_ld_32x16(taddr + c, v);
+          tmem_ld_wait();
+          uint4 pk[2];
+          __half2* h2 = reinterpret_cast<__half2*>(pk);
+#pragma unroll
+          for (int i = 0; i < 16; i += 2)
+            h2[i >> 1] = __floats2half2_rn(__uint_as_float(v[i]) * inv_sum[m], __uint_as_float(v[i + 1]) * inv_sum[m]);
+          if (c + 8 <= p.dh) *reinterpret_cast<uint4*>(orow + c) = pk[0];
+          if (c + 16 <= p.dh) *reinterpret_cast<uint4*>(orow + c + 8) = pk[1];
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(bar_done);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+PFN_encodeTiled get_encode() {
+  static PFN_encodeTiled fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_encodeTiled>(ptr);
+  });
+  return fn;
+}
+
+bool map2d(CUtensorMap* m, const void* ptr, unsigned long long cols, unsigned long long rows, unsigned box_c,
+           unsigned box_r) {
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) return false;
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {cols * 2};
+  cuuint32_t box[2] = {box_c, box_r};
+  cuuint32_t estr[2] = {1, 1};
+  return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+std::atomic<unsigned long long> g_att_launches{0};
+
+}  // namespace
+
+unsigned long long attention_launch_count() { return g_att_launches.load(); }
+
+cudaError_t launch_attention(const __half* q, const __half* k, const __half* vt, __half* out, int B, int heads, int T,
+                             int dh, float scale, cudaStream_t s, std::string* err) {
+  auto fail = [&](const char* m) {
+    if (err) *err = m;
+    return cudaErrorInvalidValue;
+  };
+  if (T != 128 && T != 256) return fail("attention: T must be 128 or 256 tokens");
+  if (dh % 8 != 0 || dh > 128 || dh < 16) return fail("attention: head_dim must be a multiple of 8 in [16, 128]");
+  AttnParams p;
+  p.n_pairs = B * heads;
+  p.heads = heads;
+  p.T = T;
+  p.dh = dh;
+  p.nkb = (dh + 63) / 64;
+  p.ksteps = (dh + 15) / 16;
+  p.npv = ((dh + 15) / 16) * 16;
+  p.n_tiles = T / 128;
+  p.scale_log2e = scale * 1.4426950408889634f;
+  p.out = out;
+  CUtensorMap mq, mk, mv;
+  const unsigned long long rows = (unsigned long long)B * heads * T;
+  if (!map2d(&mq, q, dh, rows, 64, 128) || !map2d(&mk, k, dh, rows, 64, 128) ||
+      !map2d(&mv, vt, T, (unsigned long long)B * heads * dh, 64, p.npv))
+    return fail("attention: cuTensorMapEncodeTiled failed");
+  const size_t smem = 1024 + 2 * p.nkb * 16384 + (size_t)p.nkb * T * 128 + (size_t)(T / 64) * p.npv * 128 +
+                      (size_t)(T / 64) * 16384 + 128;
+  static size_t smem_set = 0;
+  if (smem > smem_set) {
+    cudaError_t e = cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    smem_set = smem;
+  }
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int grid = p.n_pairs < sms ? p.n_pairs : sms;
+  attention_kernel<<<grid, ATT_THREADS, smem, s>>>(mq, mk, mv, p);
+  g_att_launches.fetch_add(1, std::memory_order_relaxed);
+  cudaError_t st = cudaGetLastError();
+  if (st != cudaSuccess && err) *err = std::string("attention launch: ") + cudaGetErrorString(st);
+  return st;
+}
+
+}  // namespace rgm

@@ -1,0 +1,468 @@
+// Memory-bound helper kernels around the tensor-core GEMMs: gathers, normalisation, activation, softmax, transposes
+// and the sampler's elementwise updates.  Every kernel reads/writes 16-byte vectors, consecutive lanes touching
+// consecutive addresses, with grids sized from the row count (these are all HBM-bound).
+#include <atomic>
+
+#include "aux_kernels.h"
+#include "ptx.cuh"
+
+namespace rgm {
+
+namespace {
+std::atomic<unsigned long long> g_launches{0};
+inline cudaError_t done() {
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return cudaGetLastError();
+}
+inline int blocks_for(long long n, int per_block, int cap = 148 * 16) {
+  long long b = (n + per_block - 1) / per_block;
+  if (b < 1) b = 1;
+  return (int)(b < cap ? b : cap);
+}
+}  // namespace
+
+unsigned long long aux_launch_count() { return g_launches.load(); }
+
+// ------------------------------------------------------------------------------------------------------------
+// DiT
+// ------------------------------------------------------------------------------------------------------------
+__global__ void patchify_kernel(const float* __restrict__ x, __half* __restrict__ tok, int B, int C, int H, int W,
+                                int P, int kpad) {
+  const int tpt = W / P;
+  const long long total = (long long)B * H * tpt * kpad;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int f = (int)(i % kpad);
+    const long long row = i / kpad;
+    const int part = (int)(row % tpt);
+    const long long bt = row / tpt;
+    const int time = (int)(bt % H);
+    const int b = (int)(bt / H);
+    float v = 0.f;
+    if (f < C * P) {
+      const int pl = f / C, ch = f - pl * C;
+      v = x[(((long long)b * C + ch) * H + time) * W + part * P + pl];
+    }
+    tok[i] = __float2half_rn(v);
+  }
+}
+
+cudaError_t launch_patchify(const float* x, __half* tok, int B, int C, int H, int W, int P, int kpad,
+                            cudaStream_t s) {
+  const long long total = (long long)B * H * (W / P) * kpad;
+  patchify_kernel<<<blocks_for(total, 256), 256, 0, s>>>(x, tok, B, C, H, W, P, kpad);
+  return done();
+}
+
+__global__ void timestep_embedding_kernel(const float* __restrict__ t, const float* __restrict__ freqs,
+                                          __half* __restrict__ emb, int B, int half, int ld) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * half) return;
+  const int b = i / half, j = i - b * half;
+  const float a = t[b] * freqs[j];
+  emb[(long long)b * ld + j] = __float2half_rn(cosf(a));
+  emb[(long long)b * ld + half + j] = __float2half_rn(sinf(a));
+}
+
+cudaError_t launch_timestep_embedding(const float* t, const float* freqs, __half* emb, int B, int half, int ld,
+                                      cudaStream_t s) {
+  timestep_embedding_kernel<<<(B * half + 255) / 256, 256, 0, s>>>(t, freqs, emb, B, half, ld);
+  return done();
+}
+
+__global__ void rope_table_kernel(const float* __restrict__ freqs, float* __restrict__ cosb, float* __restrict__ sinb,
+                                  int T, int nfreq) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= T * nfreq) return;
+  const int pos = i / nfreq, j = i - pos * nfreq;
+  const float a = (float)pos * freqs[j];
+  cosb[i] = cosf(a);
+  sinb[i] = sinf(a);
+}
+
+cudaError_t launch_rope_table(const float* freqs, float* cosb, float* sinb, int T, int nfreq, cudaStream_t s) {
+  rope_table_kernel<<<(T * nfreq + 255) / 256, 256, 0, s>>>(freqs, cosb, sinb, T, nfreq);
+  return done();
+}
+
+// One warp per row; the row (D = 128*NV floats) lives in registers between the statistics and the apply pass, so
+// HBM sees exactly one fp32 read and one fp16 write per element.
+template <int NV>
+__global__ void __launch_bounds__(256) ln_modulate_kernel(const float* __restrict__ x, const float* __restrict__ shift,
+                                                          const float* __restrict__ scale, int mod_ld,
+                                                          __half* __restrict__ out, long long rows,
+                                                          int rows_per_sample, float eps) {
+  constexpr int D = NV * 128;
+  const int lane = threadIdx.x & 31;
+  const long long warp0 = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long row = warp0; row < rows; row += nwarps) {
+    const float4* xr = reinterpret_cast<const float4*>(x + row * D);
+    float4 v[NV];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      v[i] = xr[i * 32 + lane];
+      s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float mean = s * (1.0f / D);
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+      q += (a * a + b * b) + (c * c + d * d);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+    const float rstd = rsqrtf(q * (1.0f / D) + eps);
+    const long long b = row / rows_per_sample;
+    const float4* sh = reinterpret_cast<const float4*>(shift + b * mod_ld);
+    const float4* sc = reinterpret_cast<const float4*>(scale + b * mod_ld);
+    uint2* o2 = reinterpret_cast<uint2*>(out + row * D);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const float4 h = __ldg(sh + i * 32 + lane);
+      const float4 c = __ldg(sc + i * 32 + lane);
+      const float y0 = (v[i].x - mean) * rstd * (1.f + c.x) + h.x;
+      const float y1 = (v[i].y - mean) * rstd * (1.f + c.y) + h.y;
+      const float y2 = (v[i].z - mean) * rstd * (1.f + c.z) + h.z;
+      const float y3 = (v[i].w - mean) * rstd * (1.f + c.w) + h.w;
+      __half2 p0 = __floats2half2_rn(y0, y1), p1 = __floats2half2_rn(y2, y3);
+      uint2 u;
+      u.x = *reinterpret_cast<uint32_t*>(&p0);
+      u.y = *reinterpret_cast<uint32_t*>(&p1);
+      o2[i * 32 + lane] = u;
+    }
+  }
+}
+
+cudaError_t launch_ln_modulate(const float* x, const float* shift, const float* scale, int mod_ld, __half* out,
+                               long long rows, int D, int rows_per_sample, float eps, cudaStream_t s) {
+  const int grid = blocks_for(rows, 8, 148 * 8);
+#define RGM_LN(NV)                                                                                                   \
+  case NV:                                                                                                           \
+    ln_modulate_kernel<NV><<<grid, 256, 0, s>>>(x, shift, scale, mod_ld, out, rows, rows_per_sample, eps);           \
+    break;
+  switch (D / 128) {
+    RGM_LN(2) RGM_LN(3) RGM_LN(4) RGM_LN(6) RGM_LN(8) RGM_LN(9)
+    default:
+      return cudaErrorInvalidValue;
+  }
+#undef RGM_LN
+  if (D % 128 != 0) return cudaErrorInvalidValue;
+  return done();
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// VAE decoder
+// ------------------------------------------------------------------------------------------------------------
+// One block per VAE tile.  z tile pixel (row = latent pitch p, col = latent time tau) = lat[cand, c, k*16+tau, p]
+// (gaussian_diffusion.py:1350-1353: permute(0,1,3,2), chunk along time, concatenate on batch).
+__global__ void __launch_bounds__(256) vae_stem_kernel(const float* __restrict__ lat, float scale,
+                                                       const float* __restrict__ pq_w, const float* __restrict__ pq_b,
+                                                       const float* __restrict__ cin_w, const float* __restrict__ cin_b,
+                                                       __half* __restrict__ out, int n_cand, int Hlat, int tile0,
+                                                       int Cout) {
+  __shared__ float zq[18][18][4];  // post_quant output with the zero halo conv_in pads with
+  __shared__ float wsm[64][36];    // conv_in weights of the 64 output channels being produced
+  __shared__ float bsm[64];
+  const int g = tile0 + blockIdx.x;
+  const int kt = g / n_cand, cand = g - kt * n_cand;
+  for (int i = threadIdx.x; i < 18 * 18 * 4; i += blockDim.x) (&zq[0][0][0])[i] = 0.f;
+  __syncthreads();
+  {
+    const int pix = threadIdx.x;  // 256 pixels
+    const int r = pix >> 4, c = pix & 15;
+    float z[4];
+#pragma unroll
+    for (int ch = 0; ch < 4; ++ch)
+      z[ch] = lat[(((long long)cand * 4 + ch) * Hlat + kt * 16 + c) * 16 + r] / scale;
+#pragma unroll
+    for (int o = 0; o < 4; ++o) {
+      float a = pq_b[o];
+#pragma unroll
+      for (int ch = 0; ch < 4; ++ch) a += pq_w[o * 4 + ch] * z[ch];
+      zq[r + 1][c + 1][o] = a;
+    }
+  }
+  __syncthreads();
+  const int pix = threadIdx.x;
+  const int r = pix >> 4, c = pix & 15;
+  float in[36];
+#pragma unroll
+  for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+    for (int kx = 0; kx < 3; ++kx)
+#pragma unroll
+      for (int ch = 0; ch < 4; ++ch) in[ch * 9 + ky * 3 + kx] = zq[r + ky][c + kx][ch];
+  __half* orow = out + ((long long)blockIdx.x * 256 + pix) * Cout;
+  for (int co0 = 0; co0 < Cout; co0 += 64) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < 64 * 36; i += blockDim.x) wsm[i / 36][i % 36] = cin_w[(long long)co0 * 36 + i];
+    if (threadIdx.x < 64) bsm[threadIdx.x] = cin_b[co0 + threadIdx.x];
+    __syncthreads();
+#pragma unroll 2
+    for (int j = 0; j < 64; j += 8) {
+      uint4 pk;
+      __half2* h2 = reinterpret_cast<__half2*>(&pk);
+#pragma unroll
+      for (int u = 0; u < 8; u += 2) {
+        float a0 = bsm[j + u], a1 = bsm[j + u + 1];
+#pragma unroll
+        for (int q = 0; q < 36; ++q) {
+          a0 += wsm[j + u][q] * in[q];
+          a1 += wsm[j + u + 1][q] * in[q];
+        }
+        h2[u >> 1] = __floats2half2_rn(a0, a1);
+      }
+      *reinterpret_cast<uint4*>(orow + co0 + j) = pk;
+    }
+  }
+}
+
+cudaError_t launch_vae_stem(const float* lat, float scale, const float* pq_w, const float* pq_b,
+                            const float* cin_w, const float* cin_b, __half* out, int n_cand, int Hlat, int tile0,
+                            int n_tiles, int Cout, cudaStream_t s) {
+  if (Cout % 64 != 0 || n_tiles <= 0) return cudaErrorInvalidValue;
+  vae_stem_kernel<<<n_tiles, 256, 0, s>>>(lat, scale, pq_w, pq_b, cin_w, cin_b, out, n_cand, Hlat, tile0, Cout);
+  return done();
+}
+
+// GroupNorm statistics straight from the tensor: one block per (image, 8-channel slab); used where no conv epilogue
+// produced partial sums (the stem output).  Accumulates in fp32 per thread, double across the block.
+__global__ void __launch_bounds__(256) gn_stats_kernel(const __half* __restrict__ x, const float* __restrict__ gamma,
+                                                       const float* __restrict__ beta, float2* __restrict__ ab, int HW,
+                                                       int C, float eps) {
+  const int img = blockIdx.y, grp = blockIdx.x;
+  const int cpg = C / 32;  // channels per group: 4, 8 or 16
+  const __half* base = x + (long long)img * HW * C + grp * cpg;
+  float s = 0.f, q = 0.f;
+  for (int i = threadIdx.x; i < HW * cpg; i += blockDim.x) {
+    const int p = i / cpg, c = i - p * cpg;
+    const float v = __half2float(base[(long long)p * C + c]);
+    s += v;
+    q += v * v;
+  }
+  __shared__ double ss[256], qq[256];
+  ss[threadIdx.x] = s;
+  qq[threadIdx.x] = q;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) {
+      ss[threadIdx.x] += ss[threadIdx.x + o];
+      qq[threadIdx.x] += qq[threadIdx.x + o];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x < cpg) {
+    const double n = (double)HW * cpg;
+    const double mean = ss[0] / n;
+    const double var = qq[0] / n - mean * mean;
+    const float rstd = (float)(1.0 / sqrt((var > 0 ? var : 0) + (double)eps));
+    const int c = grp * cpg + threadIdx.x;
+    const float a = rstd * gamma[c];
+    ab[(long long)img * C + c] = make_float2(a, beta[c] - (float)mean * a);
+  }
+}
+
+cudaError_t launch_gn_stats(const __half* x, const float* gamma, const float* beta, float2* ab, int n, int HW, int C,
+                            float eps, cudaStream_t s) {
+  if (C % 32 != 0) return cudaErrorInvalidValue;
+  gn_stats_kernel<<<dim3(32, n), 256, 0, s>>>(x, gamma, beta, ab, HW, C, eps);
+  return done();
+}
+
+// Fold the conv epilogue's per-(32 rows x 4 channels) partial sums into per-(image, group) statistics in a fixed
+// order (deterministic), in double, and emit the per-channel affine.
+__global__ void __launch_bounds__(128) gn_finalize_kernel(const float* __restrict__ part,
+                                                          const float* __restrict__ gamma,
+                                                          const float* __restrict__ beta, float2* __restrict__ ab,
+                                                          int slots_per_img, int n_par, long long par_stride, int C,
+                                                          int HW_out, float eps) {
+  const int img = blockIdx.y, grp = blockIdx.x;
+  const int qpg = C / 128;  // 4-channel quads per group (1, 2 or 4)
+  const int nq = C / 4;
+  const float2* p2 = reinterpret_cast<const float2*>(part);
+  double s = 0.0, q = 0.0;
+  const int items = n_par * slots_per_img * qpg;
+  for (int i = threadIdx.x; i < items; i += blockDim.x) {
+    const int qi = i % qpg;
+    const int sl = (i / qpg) % slots_per_img;
+    const int par = i / (qpg * slots_per_img);
+    const long long slot = par * par_stride + (long long)img * slots_per_img + sl;
+    const float2 v = p2[slot * nq + grp * qpg + qi];
+    s += v.x;
+    q += v.y;
+  }
+  __shared__ double ss[128], qq[128];
+  ss[threadIdx.x] = s;
+  qq[threadIdx.x] = q;
+  __syncthreads();
+  for (int o = 64; o > 0; o >>= 1) {
+    if (threadIdx.x < o) {
+      ss[threadIdx.x] += ss[threadIdx.x + o];
+      qq[threadIdx.x] += qq[threadIdx.x + o];
+    }
+    __syncthreads();
+  }
+  const int cpg = C / 32;
+  if (threadIdx.x < cpg) {
+    const double n = (double)HW_out * cpg;
+    const double mean = ss[0] / n;
+    const double var = qq[0] / n - mean * mean;
+    const float rstd = (float)(1.0 / sqrt((var > 0 ? var : 0) + (double)eps));
+    const int c = grp * cpg + threadIdx.x;
+    const float a = rstd * gamma[c];
+    ab[(long long)img * C + c] = make_float2(a, beta[c] - (float)mean * a);
+  }
+}
+
+cudaError_t launch_gn_finalize(const float* part, const float* gamma, const float* beta, float2* ab, int n,
+                               int slots_per_img, int n_par, long long par_stride, int C, int HW_out, float eps,
+                               cudaStream_t s) {
+  if (C % 128 != 0) return cudaErrorInvalidValue;
+  gn_finalize_kernel<<<dim3(32, n), 128, 0, s>>>(part, gamma, beta, ab, slots_per_img, n_par, par_stride, C, HW_out,
+                                                 eps);
+  return done();
+}
+
+__global__ void __launch_bounds__(256) gn_apply_kernel(const __half* __restrict__ x, const float2* __restrict__ ab,
+                                                       __half* __restrict__ y, long long total_vec, int HW, int C,
+                                                       int swish) {
+  const int cv = C >> 3;  // 8-channel vectors per pixel
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total_vec;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c8 = (int)(i % cv);
+    const long long pix = i / cv;
+    const long long img = pix / HW;
+    const uint4 u = __ldg(reinterpret_cast<const uint4*>(x) + i);
+    const float4* abp = reinterpret_cast<const float4*>(ab + img * C + c8 * 8);
+    const __half2* h2 = reinterpret_cast<const __half2*>(&u);
+    uint4 o;
+    __half2* o2 = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float4 t = __ldg(abp + j);  // (a0, b0, a1, b1)
+      const float2 f = __half22float2(h2[j]);
+      float v0 = t.x * f.x + t.y, v1 = t.z * f.y + t.w;
+      if (swish) {
+        v0 = __fdividef(v0, 1.0f + __expf(-v0));
+        v1 = __fdividef(v1, 1.0f + __expf(-v1));
+      }
+      o2[j] = __floats2half2_rn(v0, v1);
+    }
+    reinterpret_cast<uint4*>(y)[i] = o;
+  }
+}
+
+cudaError_t launch_gn_apply(const __half* x, const float2* ab, __half* y, int n, int HW, int C, int swish,
+                            cudaStream_t s) {
+  if (C % 8 != 0) return cudaErrorInvalidValue;
+  const long long total_vec = (long long)n * HW * (C / 8);
+  gn_apply_kernel<<<blocks_for(total_vec, 256 * 4, 148 * 16), 256, 0, s>>>(x, ab, y, total_vec, HW, C, swish);
+  return done();
+}
+
+// warp per row, cols <= 1024 and a multiple of 32
+__global__ void __launch_bounds__(256) softmax_rows_kernel(const float* __restrict__ x, __half* __restrict__ y,
+                                                           long long rows, int cols) {
+  const int lane = threadIdx.x & 31;
+  const long long warp0 = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const int per = cols >> 5;  // <= 32
+  for (long long row = warp0; row < rows; row += nwarps) {
+    const float* xr = x + row * cols;
+    float v[32];
+    float m = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < 32; ++i)
+      if (i < per) {
+        v[i] = xr[i * 32 + lane];
+        m = fmaxf(m, v[i]);
+      }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 32; ++i)
+      if (i < per) {
+        v[i] = __expf(v[i] - m);
+        s += v[i];
+      }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float inv = 1.0f / s;
+#pragma unroll
+    for (int i = 0; i < 32; ++i)
+      if (i < per) y[row * cols + i * 32 + lane] = __float2half_rn(v[i] * inv);
+  }
+}
+
+cudaError_t launch_softmax_rows(const float* x, __half* y, long long rows, int cols, cudaStream_t s) {
+  if (cols % 32 != 0 || cols > 1024) return cudaErrorInvalidValue;
+  softmax_rows_kernel<<<blocks_for(rows, 8, 148 * 8), 256, 0, s>>>(x, y, rows, cols);
+  return done();
+}
+
+__global__ void transpose_kernel(const __half* __restrict__ x, __half* __restrict__ y, int R, int C) {
+  __shared__ __half tile[32][33];
+  const long long base = (long long)blockIdx.z * R * C;
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  for (int j = threadIdx.y; j < 32; j += blockDim.y)
+    tile[j][threadIdx.x] = x[base + (long long)(r0 + j) * C + c0 + threadIdx.x];
+  __syncthreads();
+  for (int j = threadIdx.y; j < 32; j += blockDim.y)
+    y[base + (long long)(c0 + j) * R + r0 + threadIdx.x] = tile[threadIdx.x][j];
+}
+
+cudaError_t launch_transpose(const __half* x, __half* y, int n, int R, int C, cudaStream_t s) {
+  if (R % 32 != 0 || C % 32 != 0) return cudaErrorInvalidValue;
+  transpose_kernel<<<dim3(C / 32, R / 32, n), dim3(32, 8), 0, s>>>(x, y, R, C);
+  return done();
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// sampler elementwise
+// ------------------------------------------------------------------------------------------------------------
+__global__ void scg_fanout_kernel(const float* __restrict__ mean, const float* __restrict__ g,
+                                  const float* __restrict__ noise, float* __restrict__ cand, int N, int B,
+                                  long long elems) {
+  const long long per_n = (long long)B * elems;
+  const long long total = per_n * N;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long j = i % per_n;
+    const int b = (int)(j / elems);
+    cand[i] = mean[j] + g[b] * noise[i];
+  }
+}
+
+cudaError_t launch_scg_fanout(const float* mean, const float* g, const float* noise, float* cand, int N, int B,
+                              long long elems, cudaStream_t s) {
+  scg_fanout_kernel<<<blocks_for((long long)N * B * elems, 256), 256, 0, s>>>(mean, g, noise, cand, N, B, elems);
+  return done();
+}
+
+__global__ void x0_from_eps_kernel(const float* __restrict__ x, const float* __restrict__ eps,
+                                   const float* __restrict__ a, const float* __restrict__ c, float* __restrict__ x0,
+                                   long long total, long long elems, int clamp) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int b = (int)(i / elems);
+    // same two roundings as the reference's a*x - c*eps (two products, one subtraction; no fused multiply-add)
+    float v = __fsub_rn(__fmul_rn(a[b], x[i]), __fmul_rn(c[b], eps[i]));
+    if (clamp) v = fminf(fmaxf(v, -1.f), 1.f);
+    x0[i] = v;
+  }
+}
+
+cudaError_t launch_x0_from_eps(const float* x, const float* eps, const float* a, const float* c, float* x0, int B,
+                               long long elems, int clamp, cudaStream_t s) {
+  const long long total = (long long)B * elems;
+  x0_from_eps_kernel<<<blocks_for(total, 256), 256, 0, s>>>(x, eps, a, c, x0, total, elems, clamp);
+  return done();
+}
+
+}  // namespace rgm

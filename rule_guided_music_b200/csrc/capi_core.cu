@@ -5,6 +5,7 @@
 
 #include "../../include/rgm_b200.h"
 #include "api_util.h"
+#include "aux_kernels.h"
 #include "gemm_host.h"
 
 namespace rgm {
@@ -58,6 +59,13 @@ __global__ void pack_conv_weight_kernel(const float* __restrict__ w, __half* __r
   }
 }
 
+cudaError_t launch_pack_conv_weight(const float* w32, __half* w16, int Cout, int Cin, int cout_pad, int cin_pad,
+                                    int kind, cudaStream_t st) {
+  pack_conv_weight_kernel<<<296, 256, 0, st>>>(w32, w16, Cout, Cin, cout_pad, cin_pad, kind);
+  g_aux_launches++;
+  return cudaGetLastError();
+}
+
 }  // namespace rgm
 
 using namespace rgm;
@@ -66,7 +74,10 @@ extern "C" {
 
 const char* rgm_last_error(void) { return g_last_error.c_str(); }
 int rgm_version(void) { return 100; }
-unsigned long long rgm_launch_count(void) { return gemm_launch_count() + g_aux_launches.load(); }
+unsigned long long rgm_launch_count(void) {
+  return gemm_launch_count() + g_aux_launches.load() + aux_launch_count() + attention_launch_count() +
+         rules_launch_count();
+}
 
 int rgm_check_device(void) {
   // cudaGetDeviceProperties costs milliseconds: query each device once.
@@ -151,10 +162,9 @@ int rgm_pack_conv_weight(const float* w32, void* w16_packed, int Cout, int Cin, 
                          void* stream) {
   if (rgm_check_device()) return -1;
   if (kind < 0 || kind > 2 || cin_pad < Cin || cout_pad < Cout) return set_error("rgm_pack_conv_weight: bad arguments");
-  pack_conv_weight_kernel<<<296, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      w32, static_cast<__half*>(w16_packed), Cout, Cin, cout_pad, cin_pad, kind);
-  g_aux_launches++;
-  return check_cuda(cudaGetLastError(), "rgm_pack_conv_weight");
+  return check_cuda(launch_pack_conv_weight(w32, static_cast<__half*>(w16_packed), Cout, Cin, cout_pad, cin_pad, kind,
+                                            static_cast<cudaStream_t>(stream)),
+                    "rgm_pack_conv_weight");
 }
 
 }  // extern "C"

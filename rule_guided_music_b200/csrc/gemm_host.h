@@ -19,6 +19,7 @@ struct GemmDesc {
   // A operand: fp16 [n_img, H, W, C] with pixel stride lda (elements, >= C, multiple of 8)
   const __half* A = nullptr;
   int n_img = 1, H = 1, W = 1, C = 0, lda = 0;
+  long long a_rows = 0;  // linear layers (H == 1, n_img == 1): rows actually allocated behind A (>= W); 0 = W
   // B operand: fp16 [b_batch][rows_b][K]; K = taps * C; rows_b = num_par * N (N padded to the N tile)
   const __half* B = nullptr;
   int rows_b = 0, b_batch = 1;
@@ -36,5 +37,9 @@ cudaError_t launch_gemm(const GemmDesc& d, cudaStream_t stream, std::string* err
 unsigned long long gemm_launch_count();
 
 int device_sm_count();
+
+// fp32 [Cout,Cin,kh,kw] -> packed fp16 rows (capi_core.cu)
+cudaError_t launch_pack_conv_weight(const float* w32, __half* w16, int Cout, int Cin, int cout_pad, int cin_pad,
+                                    int kind, cudaStream_t st);
 
 }  // namespace rgm

@@ -140,7 +140,9 @@ cudaError_t launch_gemm(const GemmDesc& d, cudaStream_t stream, std::string* err
 
   GemmParams p;
   std::memset(&p, 0, sizeof(p));
-  const int bw = d.W < 128 ? d.W : 128;
+  // a linear layer (H == 1) always uses 128-row boxes; rows past the end of A are zero-filled by TMA and masked
+  // in the epilogue.  Images use full-width boxes of bh rows.
+  const int bw = (d.H == 1 || d.W >= 128) ? 128 : d.W;
   if (128 % bw != 0) return fail("gemm: W must divide 128 or be >= 128");
   const int bh = 128 / bw;
   if (bh > 1 && d.H % bh != 0) return fail("gemm: H not a multiple of the tile height");
@@ -190,8 +192,10 @@ cudaError_t launch_gemm(const GemmDesc& d, cudaStream_t stream, std::string* err
 
   CUtensorMap ma, mb;
   {
-    cuuint64_t dims[4] = {(cuuint64_t)d.C, (cuuint64_t)d.W, (cuuint64_t)d.H, (cuuint64_t)d.n_img};
-    cuuint64_t strides[3] = {(cuuint64_t)d.lda * 2, (cuuint64_t)d.W * d.lda * 2, (cuuint64_t)d.H * d.W * d.lda * 2};
+    cuuint64_t wdim = (cuuint64_t)d.W;
+    if (d.H == 1 && d.n_img == 1 && d.a_rows > d.W) wdim = (cuuint64_t)d.a_rows;
+    cuuint64_t dims[4] = {(cuuint64_t)d.C, wdim, (cuuint64_t)d.H, (cuuint64_t)d.n_img};
+    cuuint64_t strides[3] = {(cuuint64_t)d.lda * 2, wdim * d.lda * 2, (cuuint64_t)d.H * wdim * d.lda * 2};
     cuuint32_t box[4] = {GEMM_BLOCK_K, (cuuint32_t)bw, (cuuint32_t)bh, 1};
     if (!make_map(&ma, d.A, 4, dims, strides, box, err)) return cudaErrorInvalidValue;
   }

@@ -16,7 +16,7 @@ enum EpiKind : int {
   EPI_F16 = 0,         // out16[orow, n] = act(alpha*acc + bias[n] + addtab[addidx[row], n]) + resid16[orow, n]
   EPI_F32 = 1,         // out32[orow, n] = act(alpha*acc + bias[n] + addtab[addidx[row], n])
   EPI_GATE_RESID = 2,  // x32[row, n] += gate[row / rows_per_sample, n] * (acc + bias[n])
-  EPI_QKV_ROPE = 3,    // + bias, rotary on q,k, scatter to [B, heads, T, dh_pad] fp16
+  EPI_QKV_ROPE = 3,    // + bias, rotary on q,k, scatter q,k to [B, heads, T, dh_pad] and v to [B, heads, dh, T] fp16
   EPI_UNPATCH = 4,     // final layer: + bias, scatter tokens back to NCHW fp32 latent
   EPI_ROLL = 5,        // conv_out: + bias, scatter VAE tiles into the piano roll [cand, ch, 128, L] fp32
 };
@@ -213,9 +213,18 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, int row, int
           x0 = y0;
           x1 = y1;
         }
-        __half* base = which == 0 ? e.q : (which == 1 ? e.k : e.v);
-        __half2* dst = reinterpret_cast<__half2*>(base + (((long long)b * e.heads + head) * e.T + tok) * e.dh_pad + d);
-        *dst = __floats2half2_rn(x0, x1);
+        if (which == 2) {
+          // V is stored transposed, [B, heads, dh, T]: it is the K-major B operand of the P.V MMA (attention.cu).
+          // Consecutive lanes hold consecutive tokens, so each 2-byte store instruction covers 64 contiguous bytes.
+          __half* vt = e.v + (((long long)b * e.heads + head) * e.dh + d) * e.T + tok;
+          vt[0] = __float2half_rn(x0);
+          vt[e.T] = __float2half_rn(x1);
+        } else {
+          __half* base = which == 0 ? e.q : e.k;
+          __half2* dst =
+              reinterpret_cast<__half2*>(base + (((long long)b * e.heads + head) * e.T + tok) * e.dh_pad + d);
+          *dst = __floats2half2_rn(x0, x1);
+        }
       }
     }
   } else if constexpr (EPI == EPI_UNPATCH) {

@@ -1,0 +1,472 @@
+// taming KL-VAE decoder on sm_100a (reference taming/models/klvae_pedal.py:80-85 and
+// taming/modules/diffusionmodules/model.py:436-537): post_quant_conv + Decoder, driven per chunk of 16x16 latent
+// tiles, activations NHWC fp16, every convolution an implicit GEMM on tcgen05 (gemm_tc.cuh) with
+//   - bias and the ResnetBlock / AttnBlock residual add in the epilogue             model.py:117-137, 168-192
+//   - GroupNorm partial statistics of the stored tensor emitted by the epilogue     model.py:34-35
+//   - nearest-2x upsample folded into the convolution (4 parity sub-convolutions)   model.py:49-53
+//   - conv_out scattering straight into the piano roll [cand, ch, 128, 8*Hlat]      gaussian_diffusion.py:1355
+// GroupNorm apply + swish is one fp16 -> fp16 pass (aux_kernels.cu).  The latent re-tiling of _decode
+// (gaussian_diffusion.py:1347-1358), post_quant_conv and conv_in are one fp32 kernel.
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/rgm_b200.h"
+#include "api_util.h"
+#include "aux_kernels.h"
+#include "gemm_host.h"
+
+namespace rgm {
+
+
+namespace {
+
+struct Conv {
+  int cin = 0, cout = 0, k = 3, cout_pad = 0;
+  int kind = CONV_3x3;
+  __half* w = nullptr;  // packed
+  float* b = nullptr;   // [cout_pad]
+};
+struct Norm {
+  int c = 0;
+  float *gamma = nullptr, *beta = nullptr;
+};
+struct Res {
+  Norm n1, n2;
+  Conv c1, c2, nin;
+  bool has_nin = false;
+};
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t bytes = 0;
+  cudaError_t reserve(size_t need) {
+    if (need <= bytes) return cudaSuccess;
+    if (p) {
+      cudaError_t e = cudaDeviceSynchronize();
+      if (e != cudaSuccess) return e;
+      cudaFree(p);
+      p = nullptr;
+      bytes = 0;
+    }
+    cudaError_t e = cudaMalloc(&p, need);
+    if (e == cudaSuccess) bytes = need;
+    return e;
+  }
+  ~DevBuf() {
+    if (p) cudaFree(p);
+  }
+};
+
+}  // namespace
+
+struct Vae {
+  int ch = 128, n_levels = 4, nres = 2, zc = 4, out_ch = 3;
+  std::vector<int> mult;
+  // stem (fp32)
+  float *pq_w = nullptr, *pq_b = nullptr, *cin_w = nullptr, *cin_b = nullptr;
+  int block_in0 = 0;
+  Res mid1, mid2;
+  Norm attn_norm;
+  Conv attn_q, attn_k, attn_v, attn_proj;
+  std::vector<std::vector<Res>> up;     // [level][block]
+  std::vector<Conv> upsample;           // [level] (level 0 unused)
+  Norm norm_out;
+  Conv conv_out;
+  std::map<std::string, std::pair<float*, long long>> f32_keys;  // key -> (dst, numel)
+  std::map<std::string, Conv*> conv_keys;                        // "<name>.weight" -> conv
+  std::vector<void*> allocs;
+  DevBuf act[4], gnpart, abbuf, attn_s;
+  int chunk_tiles = 128;
+
+  ~Vae() {
+    for (void* p : allocs) cudaFree(p);
+  }
+  template <typename T>
+  T* alloc(long long n) {
+    void* p = nullptr;
+    if (cudaMalloc(&p, (size_t)n * sizeof(T)) != cudaSuccess) return nullptr;
+    cudaMemset(p, 0, (size_t)n * sizeof(T));
+    allocs.push_back(p);
+    return static_cast<T*>(p);
+  }
+  bool make_conv(Conv& c, const std::string& name, int cin, int cout, int k, int kind) {
+    c.cin = cin;
+    c.cout = cout;
+    c.k = k;
+    c.kind = kind;
+    c.cout_pad = cout % 128 == 0 ? cout : (int)((cout + 31) / 32 * 32);
+    const int taps = kind == CONV_1x1 ? 1 : (kind == CONV_3x3 ? 9 : 4);
+    const int npar = kind == CONV_UP2 ? 4 : 1;
+    c.w = alloc<__half>((long long)npar * c.cout_pad * taps * cin);
+    c.b = alloc<float>(c.cout_pad);
+    if (!c.w || !c.b) return false;
+    conv_keys[name + ".weight"] = &c;
+    f32_keys[name + ".bias"] = {c.b, cout};
+    return true;
+  }
+  bool make_norm(Norm& n, const std::string& name, int c) {
+    n.c = c;
+    n.gamma = alloc<float>(c);
+    n.beta = alloc<float>(c);
+    if (!n.gamma || !n.beta) return false;
+    f32_keys[name + ".weight"] = {n.gamma, c};
+    f32_keys[name + ".bias"] = {n.beta, c};
+    return true;
+  }
+  bool make_res(Res& r, const std::string& p, int cin, int cout) {
+    r.has_nin = cin != cout;
+    bool ok = make_norm(r.n1, p + ".norm1", cin) && make_conv(r.c1, p + ".conv1", cin, cout, 3, CONV_3x3) &&
+              make_norm(r.n2, p + ".norm2", cout) && make_conv(r.c2, p + ".conv2", cout, cout, 3, CONV_3x3);
+    if (ok && r.has_nin) ok = make_conv(r.nin, p + ".nin_shortcut", cin, cout, 1, CONV_1x1);
+    return ok;
+  }
+};
+
+namespace {
+
+int vae_build(Vae* m) {
+  int block_in = m->ch * m->mult[m->n_levels - 1];
+  m->block_in0 = block_in;
+  m->pq_w = m->alloc<float>(m->zc * m->zc);
+  m->pq_b = m->alloc<float>(m->zc);
+  m->cin_w = m->alloc<float>((long long)block_in * m->zc * 9);
+  m->cin_b = m->alloc<float>(block_in);
+  if (!m->pq_w || !m->pq_b || !m->cin_w || !m->cin_b) return set_error("rgm_vae_create: out of memory");
+  m->f32_keys["post_quant_conv.weight"] = {m->pq_w, (long long)m->zc * m->zc};
+  m->f32_keys["post_quant_conv.bias"] = {m->pq_b, m->zc};
+  m->f32_keys["decoder.conv_in.weight"] = {m->cin_w, (long long)block_in * m->zc * 9};
+  m->f32_keys["decoder.conv_in.bias"] = {m->cin_b, block_in};
+  bool ok = m->make_res(m->mid1, "decoder.mid.block_1", block_in, block_in) &&
+            m->make_norm(m->attn_norm, "decoder.mid.attn_1.norm", block_in) &&
+            m->make_conv(m->attn_q, "decoder.mid.attn_1.q", block_in, block_in, 1, CONV_1x1) &&
+            m->make_conv(m->attn_k, "decoder.mid.attn_1.k", block_in, block_in, 1, CONV_1x1) &&
+            m->make_conv(m->attn_v, "decoder.mid.attn_1.v", block_in, block_in, 1, CONV_1x1) &&
+            m->make_conv(m->attn_proj, "decoder.mid.attn_1.proj_out", block_in, block_in, 1, CONV_1x1) &&
+            m->make_res(m->mid2, "decoder.mid.block_2", block_in, block_in);
+  m->up.resize(m->n_levels);
+  m->upsample.resize(m->n_levels);
+  for (int lvl = m->n_levels - 1; ok && lvl >= 0; --lvl) {
+    const int block_out = m->ch * m->mult[lvl];
+    m->up[lvl].resize(m->nres + 1);
+    for (int b = 0; ok && b <= m->nres; ++b) {
+      ok = m->make_res(m->up[lvl][b], "decoder.up." + std::to_string(lvl) + ".block." + std::to_string(b), block_in,
+                       block_out);
+      block_in = block_out;
+    }
+    if (ok && lvl != 0)
+      ok = m->make_conv(m->upsample[lvl], "decoder.up." + std::to_string(lvl) + ".upsample.conv", block_in, block_in, 3,
+                        CONV_UP2);
+  }
+  ok = ok && m->make_norm(m->norm_out, "decoder.norm_out", block_in) &&
+       m->make_conv(m->conv_out, "decoder.conv_out", block_in, m->out_ch, 3, CONV_3x3);
+  if (!ok) return set_error("rgm_vae_create: out of memory");
+  return 0;
+}
+
+struct Ctx {
+  Vae* m;
+  cudaStream_t st;
+  int nt;  // tiles in this chunk
+};
+
+#define RGM_VGEMM_OK(desc)                                                                    \
+  do {                                                                                        \
+    std::string _err;                                                                         \
+    if (launch_gemm(desc, c.st, &_err) != cudaSuccess) return set_error("rgm_vae: " + _err);  \
+  } while (0)
+
+// conv on NHWC fp16 [nt, H, H, cin] -> out [nt, H', H', cout]; optional residual; emits GroupNorm partials
+int run_conv(Ctx& c, const Conv& cv, const __half* x, int H, const __half* resid, __half* out, bool want_gn) {
+  GemmDesc d;
+  d.A = x;
+  d.n_img = c.nt;
+  d.H = H;
+  d.W = H;
+  d.C = cv.cin;
+  d.lda = cv.cin;
+  d.B = cv.w;
+  d.N = cv.cout;
+  d.rows_b = (cv.kind == CONV_UP2 ? 4 : 1) * cv.cout;
+  d.conv = cv.kind;
+  d.epi = EPI_F16;
+  d.e.out = out;
+  d.e.ldo = cv.cout;
+  d.e.bias = cv.b;
+  d.e.alpha = 1.f;
+  d.e.resid = resid;
+  d.e.ldr = cv.cout;
+  d.e.gn_part = want_gn ? static_cast<float*>(c.m->gnpart.p) : nullptr;
+  if (cv.kind == CONV_UP2) {
+    d.e.up2 = 1;
+    d.e.upH = H;
+    d.e.upW = H;
+  }
+  RGM_VGEMM_OK(d);
+  return 0;
+}
+
+// GroupNorm affine (a, b) per (tile, channel) from the partials the last run_conv wrote
+int gn_from_part(Ctx& c, const Norm& n, int H_in, bool was_up2) {
+  const int lowHW = H_in * H_in;
+  const long long par_stride = (long long)c.nt * lowHW / 32;
+  RGM_CUDA_OK(launch_gn_finalize(static_cast<float*>(c.m->gnpart.p), n.gamma, n.beta,
+                                 static_cast<float2*>(c.m->abbuf.p), c.nt, lowHW / 32, was_up2 ? 4 : 1, par_stride, n.c,
+                                 was_up2 ? 4 * lowHW : lowHW, 1e-6f, c.st));
+  return 0;
+}
+
+// ResnetBlock (model.py:117-137). x: input [nt,H,H,cin] whose GroupNorm partials are current; t, h: scratch; out may
+// alias neither x nor h.  Leaves the partials of `out` current.
+int run_res(Ctx& c, const Res& r, const __half* x, int H, bool x_from_up2, __half* t, __half* h, __half* out) {
+  const int HW = H * H;
+  if (gn_from_part(c, r.n1, x_from_up2 ? H / 2 : H, x_from_up2)) return -1;
+  RGM_CUDA_OK(launch_gn_apply(x, static_cast<float2*>(c.m->abbuf.p), t, c.nt, HW, r.n1.c, 1, c.st));
+  if (run_conv(c, r.c1, t, H, nullptr, h, true)) return -1;
+  if (gn_from_part(c, r.n2, H, false)) return -1;
+  RGM_CUDA_OK(launch_gn_apply(h, static_cast<float2*>(c.m->abbuf.p), t, c.nt, HW, r.n2.c, 1, c.st));
+  const __half* resid = x;
+  if (r.has_nin) {
+    if (run_conv(c, r.nin, x, H, nullptr, out, false)) return -1;
+    resid = out;  // conv2 adds the shortcut it finds in `out` and overwrites it (same thread reads then writes)
+  }
+  return run_conv(c, r.c2, t, H, resid, out, true);
+}
+
+int decode_chunk(Vae* m, const float* lat, float scale, float* roll, int n_cand, int Hlat, int roll_ch, int tile0,
+                 int nt, cudaStream_t st) {
+  Ctx c{m, st, nt};
+  __half* buf[4];
+  for (int i = 0; i < 4; ++i) buf[i] = static_cast<__half*>(m->act[i].p);
+  float2* ab = static_cast<float2*>(m->abbuf.p);
+  int H = 16;
+  int C = m->block_in0;
+  // stem
+  RGM_CUDA_OK(launch_vae_stem(lat, scale, m->pq_w, m->pq_b, m->cin_w, m->cin_b, buf[0], n_cand, Hlat, tile0, nt, C,
+                              st));
+  // mid.block_1: the stem has no GEMM epilogue, so its GroupNorm statistics come from a direct pass
+  {
+    const Res& r = m->mid1;
+    RGM_CUDA_OK(launch_gn_stats(buf[0], r.n1.gamma, r.n1.beta, ab, nt, H * H, C, 1e-6f, st));
+    RGM_CUDA_OK(launch_gn_apply(buf[0], ab, buf[1], nt, H * H, C, 1, st));
+    if (run_conv(c, r.c1, buf[1], H, nullptr, buf[2], true)) return -1;
+    if (gn_from_part(c, r.n2, H, false)) return -1;
+    RGM_CUDA_OK(launch_gn_apply(buf[2], ab, buf[1], nt, H * H, C, 1, st));
+    if (run_conv(c, r.c2, buf[1], H, buf[0], buf[3], true)) return -1;
+  }
+  int cur = 3;  // buf[cur] holds x
+  // mid.attn_1 (model.py:168-192): single head over the 256 positions of a tile
+  {
+    const int HW = H * H;
+    __half* x = buf[cur];
+    __half* hn = buf[0];
+    if (gn_from_part(c, m->attn_norm, H, false)) return -1;
+    RGM_CUDA_OK(launch_gn_apply(x, ab, hn, nt, HW, C, 0, st));
+    // q, k, v, v^T, P carve buf[1] and buf[2] (each holds >= 4 tensors of this size: buffers are sized for 128x128x256)
+    const long long tsz = (long long)nt * HW * C;
+    __half* q = buf[1];
+    __half* k = buf[1] + tsz;
+    __half* v = buf[1] + 2 * tsz;
+    __half* vT = buf[2];
+    __half* P = buf[2] + tsz;
+    __half* ao = buf[2] + 2 * tsz;
+    if (run_conv(c, m->attn_q, hn, H, nullptr, q, false)) return -1;
+    if (run_conv(c, m->attn_k, hn, H, nullptr, k, false)) return -1;
+    if (run_conv(c, m->attn_v, hn, H, nullptr, v, false)) return -1;
+    RGM_CUDA_OK(launch_transpose(v, vT, nt, HW, C, st));
+    float* S = static_cast<float*>(m->attn_s.p);
+    {
+      GemmDesc d;  // S[b] = q[b] k[b]^T * C^-0.5
+      d.A = q;
+      d.n_img = nt;
+      d.H = 1;
+      d.W = HW;
+      d.C = C;
+      d.lda = C;
+      d.B = k;
+      d.rows_b = HW;
+      d.b_batch = nt;
+      d.N = HW;
+      d.conv = CONV_1x1;
+      d.epi = EPI_F32;
+      d.e.out = S;
+      d.e.ldo = HW;
+      d.e.alpha = 1.0f / sqrtf((float)C);
+      RGM_VGEMM_OK(d);
+    }
+    RGM_CUDA_OK(launch_softmax_rows(S, P, (long long)nt * HW, HW, st));
+    {
+      GemmDesc d;  // ao[b] = P[b] v[b]  (B operand = v^T [C, HW])
+      d.A = P;
+      d.n_img = nt;
+      d.H = 1;
+      d.W = HW;
+      d.C = HW;
+      d.lda = HW;
+      d.B = vT;
+      d.rows_b = C;
+      d.b_batch = nt;
+      d.N = C;
+      d.conv = CONV_1x1;
+      d.epi = EPI_F16;
+      d.e.out = ao;
+      d.e.ldo = C;
+      d.e.alpha = 1.f;
+      RGM_VGEMM_OK(d);
+    }
+    if (run_conv(c, m->attn_proj, ao, H, x, hn, true)) return -1;  // x + proj_out(attention)
+    cur = 0;
+  }
+  // mid.block_2
+  {
+    const int o = (cur + 3) & 3;
+    if (run_res(c, m->mid2, buf[cur], H, false, buf[(cur + 1) & 3], buf[(cur + 2) & 3], buf[o])) return -1;
+    cur = o;
+  }
+  bool from_up = false;
+  for (int lvl = m->n_levels - 1; lvl >= 0; --lvl) {
+    for (int b = 0; b <= m->nres; ++b) {
+      const int o = (cur + 3) & 3;
+      if (run_res(c, m->up[lvl][b], buf[cur], H, from_up, buf[(cur + 1) & 3], buf[(cur + 2) & 3], buf[o])) return -1;
+      cur = o;
+      from_up = false;
+    }
+    if (lvl != 0) {
+      const int o = (cur + 1) & 3;
+      if (run_conv(c, m->upsample[lvl], buf[cur], H, nullptr, buf[o], true)) return -1;
+      cur = o;
+      H *= 2;
+      from_up = true;
+    }
+  }
+  // norm_out + swish + conv_out, scattered into the roll
+  {
+    const int HW = H * H;
+    if (gn_from_part(c, m->norm_out, from_up ? H / 2 : H, from_up)) return -1;
+    __half* t = buf[(cur + 1) & 3];
+    RGM_CUDA_OK(launch_gn_apply(buf[cur], ab, t, nt, HW, m->norm_out.c, 1, st));
+    if (H != 128) return set_error("rgm_vae: decoder output is not 128x128 (EPI_ROLL assumes 128x128 tiles)");
+    GemmDesc d;
+    d.A = t;
+    d.n_img = nt;
+    d.H = H;
+    d.W = H;
+    d.C = m->conv_out.cin;
+    d.lda = m->conv_out.cin;
+    d.B = m->conv_out.w;
+    d.N = m->conv_out.cout_pad;
+    d.rows_b = m->conv_out.cout_pad;
+    d.conv = CONV_3x3;
+    d.epi = EPI_ROLL;
+    d.block_n = 32;
+    d.e.out = roll;
+    d.e.bias = m->conv_out.b;
+    d.e.tile0 = tile0;
+    d.e.n_cand = n_cand;
+    d.e.roll_len = 8 * Hlat;
+    d.e.roll_ch = roll_ch;
+    RGM_VGEMM_OK(d);
+  }
+  return 0;
+}
+
+}  // namespace
+}  // namespace rgm
+
+using namespace rgm;
+
+extern "C" {
+
+int rgm_vae_create(rgm_vae** out, int ch, const int* ch_mult, int n_levels, int num_res_blocks, int z_channels,
+                   int out_ch) {
+  if (rgm_check_device()) return -1;
+  if (!out || !ch_mult || n_levels < 1 || n_levels > 8) return set_error("rgm_vae_create: bad arguments");
+  if (z_channels != 4) return set_error("rgm_vae_create: the fused stem is written for z_channels = 4");
+  if (out_ch > 32) return set_error("rgm_vae_create: out_ch > 32");
+  Vae* m = new Vae();
+  m->ch = ch;
+  m->n_levels = n_levels;
+  m->nres = num_res_blocks;
+  m->zc = z_channels;
+  m->out_ch = out_ch;
+  m->mult.assign(ch_mult, ch_mult + n_levels);
+  for (int i = 0; i < n_levels; ++i)
+    if ((ch * ch_mult[i]) % 128 != 0) {
+      delete m;
+      return set_error("rgm_vae_create: every level's channel count must be a multiple of 128");
+    }
+  if ((16 << (n_levels - 1)) != 128) {
+    delete m;
+    return set_error("rgm_vae_create: this build decodes 16x16 latent tiles to 128x128 (4 levels)");
+  }
+  if (const char* e = getenv("RGM_VAE_CHUNK")) m->chunk_tiles = atoi(e) > 0 ? atoi(e) : m->chunk_tiles;
+  if (vae_build(m) != 0) {
+    delete m;
+    return -1;
+  }
+  *out = reinterpret_cast<rgm_vae*>(m);
+  return 0;
+}
+
+int rgm_vae_destroy(rgm_vae* h) {
+  if (h) {
+    cudaDeviceSynchronize();
+    delete reinterpret_cast<Vae*>(h);
+  }
+  return 0;
+}
+
+int rgm_vae_load(rgm_vae* h, const char* key, const float* src, long long numel, void* stream) {
+  if (!h || !key || !src) return set_error("rgm_vae_load: null argument");
+  Vae* m = reinterpret_cast<Vae*>(h);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const std::string k(key);
+  auto f = m->f32_keys.find(k);
+  if (f != m->f32_keys.end()) {
+    if (numel != f->second.second)
+      return set_error("rgm_vae_load: " + k + ": expected " + std::to_string(f->second.second) + " elements");
+    return check_cuda(cudaMemcpyAsync(f->second.first, src, (size_t)numel * sizeof(float), cudaMemcpyDeviceToDevice, st),
+                      "rgm_vae_load");
+  }
+  auto cv = m->conv_keys.find(k);
+  if (cv == m->conv_keys.end()) return 1;  // encoder / loss / quant_conv tensors: not on this path
+  const Conv& c = *cv->second;
+  if (numel != (long long)c.cout * c.cin * c.k * c.k)
+    return set_error("rgm_vae_load: " + k + ": unexpected element count");
+  return check_cuda(launch_pack_conv_weight(src, c.w, c.cout, c.cin, c.cout_pad, c.cin, c.kind, st), "rgm_vae_load");
+}
+
+int rgm_vae_decode_latents(rgm_vae* h, const float* lat, float scale_factor, float* roll, int n_cand, int Hlat,
+                           int roll_ch, void* stream) {
+  if (rgm_check_device()) return -1;
+  if (!h || !lat || !roll) return set_error("rgm_vae_decode_latents: null argument");
+  Vae* m = reinterpret_cast<Vae*>(h);
+  if (n_cand <= 0) return 0;
+  if (Hlat % 16 != 0 || Hlat <= 0) return set_error("rgm_vae_decode_latents: latent length must be a multiple of 16");
+  if (roll_ch < 1 || roll_ch > m->out_ch) return set_error("rgm_vae_decode_latents: roll_ch out of range");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int total = n_cand * (Hlat / 16);
+  const int chunk = m->chunk_tiles < total ? m->chunk_tiles : total;
+  // the largest activation of the decoder: 128x128 pixels x (channels of level 1) per tile
+  long long maxc = 0;
+  for (int l = 0; l < m->n_levels; ++l) {
+    const long long hw = (long long)(16 << (m->n_levels - 1 - l)) * (16 << (m->n_levels - 1 - l));
+    const long long cmax = (long long)m->ch * m->mult[l < m->n_levels - 1 ? l + 1 : l];
+    maxc = std::max(maxc, hw * std::max(cmax, (long long)m->ch * m->mult[l]));
+  }
+  maxc = std::max(maxc, 4LL * 256 * m->block_in0);  // the attention block carves 3-4 tensors out of one buffer
+  for (int i = 0; i < 4; ++i) RGM_CUDA_OK(m->act[i].reserve((size_t)chunk * maxc * sizeof(__half)));
+  RGM_CUDA_OK(m->gnpart.reserve((size_t)chunk * maxc / 8 + 1024));
+  RGM_CUDA_OK(m->abbuf.reserve((size_t)chunk * 512 * sizeof(float2) * 2));
+  RGM_CUDA_OK(m->attn_s.reserve((size_t)chunk * 256 * 256 * sizeof(float)));
+  for (int t0 = 0; t0 < total; t0 += chunk) {
+    const int nt = (total - t0) < chunk ? (total - t0) : chunk;
+    if (decode_chunk(m, lat, scale_factor, roll, n_cand, Hlat, roll_ch, t0, nt, st) != 0) return -1;
+  }
+  return 0;
+}
+
+}  // extern "C"

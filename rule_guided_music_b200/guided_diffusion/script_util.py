@@ -1,0 +1,70 @@
+"""create_diffusion and the argparse helpers -- mirror of guided_diffusion/script_util.py of the reference
+(diffusion_defaults :13-26, create_diffusion :106-126, create_gaussian_diffusion :462-500, add_dict_to_argparser
+:503-513, args_to_dict :516-517, str2bool :520-531).  The UNet / classifier / super-resolution factories are not on
+the sampling path."""
+import argparse
+
+from . import gaussian_diffusion as gd
+from .respace import SpacedDiffusion, space_timesteps
+
+
+def diffusion_defaults():
+    return dict(learn_sigma=False, diffusion_steps=1000, noise_schedule="linear", timestep_respacing="", use_kl=False,
+                predict_xstart=False, rescale_timesteps=False, rescale_learned_sigmas=False)
+
+
+def create_diffusion(learn_sigma=False, diffusion_steps=1000, noise_schedule="linear", timestep_respacing="",
+                     use_kl=False, predict_xstart=False, rescale_timesteps=False, rescale_learned_sigmas=False):
+    return create_gaussian_diffusion(steps=diffusion_steps, learn_sigma=learn_sigma, noise_schedule=noise_schedule,
+                                     use_kl=use_kl, predict_xstart=predict_xstart,
+                                     rescale_timesteps=rescale_timesteps,
+                                     rescale_learned_sigmas=rescale_learned_sigmas,
+                                     timestep_respacing=timestep_respacing)
+
+
+def create_gaussian_diffusion(*, steps=1000, learn_sigma=False, sigma_small=False, noise_schedule="linear",
+                              use_kl=False, predict_xstart=False, rescale_timesteps=False,
+                              rescale_learned_sigmas=False, timestep_respacing=""):
+    betas = gd.get_named_beta_schedule(noise_schedule, steps)
+    if use_kl:
+        loss_type = gd.LossType.RESCALED_KL
+    elif rescale_learned_sigmas:
+        loss_type = gd.LossType.RESCALED_MSE
+    else:
+        loss_type = gd.LossType.MSE
+    if learn_sigma:
+        var_type = gd.ModelVarType.LEARNED_RANGE
+    else:
+        var_type = gd.ModelVarType.FIXED_SMALL if sigma_small else gd.ModelVarType.FIXED_LARGE
+    return SpacedDiffusion(
+        use_timesteps=space_timesteps(steps, timestep_respacing or [steps]),
+        betas=betas,
+        model_mean_type=gd.ModelMeanType.START_X if predict_xstart else gd.ModelMeanType.EPSILON,
+        model_var_type=var_type,
+        loss_type=loss_type,
+        rescale_timesteps=rescale_timesteps,
+    )
+
+
+def add_dict_to_argparser(parser, default_dict):
+    for k, v in default_dict.items():
+        v_type = type(v)
+        if v is None:
+            v_type = str
+        elif isinstance(v, bool):
+            v_type = str2bool
+        parser.add_argument(f"--{k}", default=v, type=v_type)
+
+
+def args_to_dict(args, keys):
+    return {k: getattr(args, k) for k in keys}
+
+
+def str2bool(v):
+    if isinstance(v, bool):
+        return v
+    if v.lower() in ("yes", "true", "t", "y", "1"):
+        return True
+    if v.lower() in ("no", "false", "f", "n", "0"):
+        return False
+    raise argparse.ArgumentTypeError("boolean value expected")

@@ -21,12 +21,12 @@ RULE_NAMES = ["pitch_hist", "note_density", "note_density_hr_1", "note_density_h
 # DiT
 # ---------------------------------------------------------------------------------------------------------------
 DIT_CASES = {
-    # small model with the XL head geometry (head_dim 72, rotary 36) so every kernel path is exercised quickly
+    # shallow model with the XL width and head geometry (head_dim 72, rotary 36): every kernel path, quickly
     "small": dict(preset=None, input_size=[128, 16], batch=3, half_tile=True,
-                  weights=dict(seed=11, depth=2, hidden=576, patch=8, heads=8, num_classes=3)),
-    # head_dim 64 (DiTRotary_B geometry), patch 16
+                  weights=dict(seed=11, depth=2, hidden=1152, patch=8, heads=16, num_classes=3)),
+    # head_dim 64 (DiTRotary_B geometry), patch 16 (one token per time step)
     "small_hd64": dict(preset=None, input_size=[128, 16], batch=2, half_tile=False,
-                       weights=dict(seed=12, depth=2, hidden=256, patch=16, heads=4, num_classes=3)),
+                       weights=dict(seed=12, depth=2, hidden=384, patch=16, heads=6, num_classes=3)),
     # the flagship: DiTRotary_XL_8 (depth 28, hidden 1152, 16 heads), reference dit.py:902
     "xl8": dict(preset="DiTRotary_XL_8", input_size=[128, 16], batch=2, half_tile=True,
                 weights=dict(seed=0, depth=28, hidden=1152, patch=8, heads=16, num_classes=3)),
@@ -109,11 +109,11 @@ SAMPLER_CASES = {
     # DDIM eta=0 / eta=1 without guidance
     "ddim_plain": dict(dit="small", respacing="ddim4", ddim=True, eta=0.0, shape=(2, 4, 128, 16), seed=4, scg=None,
                        guidance=None),
-    # DDIM(eta=1) + SCG, pitch histogram, N=3 (config-3 shape in miniature); H=32 latents = 2 VAE tiles
-    "ddim_scg_pitch": dict(dit="small", respacing="4", ddim=True, eta=1.0, shape=(2, 4, 32, 16), seed=5,
+    # DDIM(eta=1) + SCG, pitch histogram, N=3 (config-3 shape in miniature); H=64 latents = 4 VAE tiles
+    "ddim_scg_pitch": dict(dit="small", respacing="4", ddim=True, eta=1.0, shape=(2, 4, 64, 16), seed=5,
                            scg=dict(num_samples=3, pitch_hist=1.0), guidance=_GUIDE_ON, rules=["pitch_hist"]),
     # DDPM + SCG with two rules (order dependent in-place masking) and a scheduled guidance window
-    "ddpm_scg_two": dict(dit="small", respacing="6", ddim=False, shape=(2, 4, 32, 16), seed=6,
+    "ddpm_scg_two": dict(dit="small", respacing="6", ddim=False, shape=(2, 4, 64, 16), seed=6,
                          scg=dict(num_samples=2, note_density=0.5, pitch_hist=2.0), guidance=_GUIDE_SCHED,
                          rules=["pitch_hist", "note_density"]),
 }

@@ -1,0 +1,129 @@
+"""CPU-side checks of the host mirror (no GPU, no compute calls into the library): schedule tables and respacing vs
+the reference's goldens, the plain sampling loops (pure torch host logic) vs the reference trajectories with the
+oracle's denoiser as the model callable, config/registry surface, and the C ABI's exported symbols."""
+import ctypes
+import os
+import re
+from functools import partial
+
+import numpy as np
+import pytest
+import torch
+
+import golden_inputs as gi
+from oracle import dit as odit
+from oracle import weights as ow
+from rule_guided_music_b200 import _lib
+from rule_guided_music_b200.guided_diffusion import respace
+from rule_guided_music_b200.guided_diffusion.condition_functions import dc_model_fn, model_fn
+from rule_guided_music_b200.guided_diffusion.script_util import create_diffusion
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "rgm_b200.h")).read()
+    declared = set(re.findall(r"\b(rgm_[a-z0-9_]+)\s*\(", header))
+    assert len(declared) >= 20
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for name in sorted(declared):
+        assert hasattr(lib, name), name
+    assert declared == set(_lib.exported_symbols()), declared ^ set(_lib.exported_symbols())
+    assert lib.rgm_version() >= 100
+
+
+def test_no_cpu_fallback():
+    """Compute entry points refuse to run without an sm_100 device instead of falling back."""
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from rule_guided_music_b200.guided_diffusion.dit import DiT_models
+    from rule_guided_music_b200.music_rule_guidance.rule_maps import FUNC_DICT
+
+    m = DiT_models["DiTRotary_XL_8"](input_size=[128, 16], in_channels=4, num_classes=3, learn_sigma=False)
+    with pytest.raises(_lib.RgmError):
+        m.to("cpu")
+    with pytest.raises(_lib.RgmError):
+        FUNC_DICT["pitch_hist"](torch.zeros(1, 3, 128, 1024))
+    assert _lib.lib().rgm_check_device() != 0
+    assert b"no CUDA device" in _lib.lib().rgm_last_error() or b"sm_" in _lib.lib().rgm_last_error()
+
+
+def test_schedule_tables_match_reference():
+    g = np.load(os.path.join(GOLD, "schedule.npz"))
+    d = create_diffusion()
+    for k in gi.SCHEDULE_KEYS:
+        np.testing.assert_allclose(getattr(d, k), g["full_" + k], rtol=1e-15, atol=0, err_msg=k)
+    for resp in ("256", "ddim50", "4", "ddim25", "10,15,20"):
+        s = create_diffusion(timestep_respacing=resp)
+        tag = resp.replace(",", "_")
+        np.testing.assert_array_equal(np.array(s.timestep_map), g[f"resp_{tag}_map"])
+        np.testing.assert_allclose(s.betas, g[f"resp_{tag}_betas"], rtol=1e-14)
+    with pytest.raises(ValueError):
+        respace.space_timesteps(1000, "ddim256")
+    c = create_diffusion(diffusion_steps=100, noise_schedule="cosine")
+    np.testing.assert_allclose(c.betas, g["cosine100_betas"], rtol=1e-14)
+
+
+@pytest.mark.parametrize("tag", ["ddpm_plain", "ddim_plain"])
+def test_plain_loops_match_reference_on_cpu(tag):
+    """Host logic of p_sample / ddim_sample / loops, device tables and the wrapped timestep map, with the oracle DiT."""
+    g = np.load(os.path.join(GOLD, "sampler.npz"))
+    cfg = gi.SAMPLER_CASES[tag]
+    dcfg = gi.DIT_CASES[cfg["dit"]]
+    sd = ow.make_dit_state_dict(**dcfg["weights"])
+    w = dcfg["weights"]
+
+    class Oracle:
+        def __call__(self, x, t, y=None):
+            return odit.dit_forward(sd, x, t, y, heads=w["heads"], patch=w["patch"])
+
+        def parameters(self):
+            yield torch.zeros(1)
+
+    fn = partial(model_fn, model=Oracle(), num_classes=3, class_cond=True, cfg=False, w=0.0)
+    diffusion = create_diffusion(timestep_respacing=cfg["respacing"])
+    loop = diffusion.ddim_sample_loop_progressive if cfg["ddim"] else diffusion.p_sample_loop_progressive
+    extra = {"eta": cfg["eta"]} if cfg["ddim"] else {}
+    torch.manual_seed(cfg["seed"])
+    steps = [o["sample"].numpy().copy() for o in
+             loop(fn, cfg["shape"], model_kwargs=gi.sampler_model_kwargs(cfg), device="cpu", **extra)]
+    np.testing.assert_allclose(np.stack(steps), g[tag], atol=5e-5, rtol=1e-4)
+
+
+def test_model_fn_dispatch():
+    calls = []
+
+    def fake(x, t, y):
+        calls.append(y.clone())
+        return x * 0 + y.view(-1, 1, 1, 1).float()
+
+    x = torch.zeros(2, 4, 8, 16)
+    t = torch.zeros(2, dtype=torch.long)
+    y = torch.tensor([0, 2])
+    assert torch.equal(model_fn(x, t, y=y, rule={"a": 1}, model=fake)[:, 0, 0, 0], torch.tensor([0., 2.]))
+    assert torch.equal(model_fn(x, t, y=y, model=fake, class_cond=False)[:, 0, 0, 0], torch.tensor([3., 3.]))
+    out = model_fn(x, t, y=y, model=fake, cfg=True, w=2.0)  # (1+w) m(y) - w m(null)
+    assert torch.equal(out[:, 0, 0, 0], torch.tensor([3 * 0. - 2 * 3, 3 * 2. - 2 * 3]))
+    xd = torch.arange(2 * 4 * 16 * 8, dtype=torch.float32).view(2, 4, 16, 8)
+    seen = {}
+
+    def fake2(x, t, y):
+        seen["shape"] = tuple(x.shape)
+        return x
+
+    assert torch.equal(dc_model_fn(xd, t, y=y, model=fake2), xd) and seen["shape"] == (2, 4, 8, 16)
+
+
+def test_registry_and_config_surface(tmp_path):
+    from rule_guided_music_b200.guided_diffusion.dit import DiT_models
+    from rule_guided_music_b200.guided_diffusion.midi_util import load_config
+    from rule_guided_music_b200.music_rule_guidance.rule_maps import FUNC_DICT, LOSS_DICT
+
+    m = DiT_models["DiTRotary_XL_8"](input_size=[128, 16], in_channels=4, num_classes=3, learn_sigma=False)
+    assert (m.depth, m.hidden_size, m.num_heads, m.patch_size, m.label_rows, m.out_channels) == (28, 1152, 16, 8, 4, 4)
+    assert set(FUNC_DICT) == set(LOSS_DICT) and "pitch_hist" in FUNC_DICT
+    p = tmp_path / "c.yml"
+    p.write_text("guidance:\n  schedule: true\n  t_start: 750\nscg:\n  num_samples: 16\n  pitch_hist: 1.0\n")
+    c = load_config(str(p))
+    assert c.guidance.t_start == 750 and vars(c.scg)["num_samples"] == 16

@@ -1,0 +1,54 @@
+"""taming VAE decoder on the B200 vs the reference's outputs (tests/golden/vae.npz) and the oracle.
+
+Activations are stored in fp16 between layers and conv operands are fp16 (fp32 accumulate); the reference runs its
+convolutions in TF32 on a GPU and fp32 on the CPU.  Bar: 5e-3 relative L2 of the decoded roll and at most 0.5 % of
+pixels on the other side of the rules' -0.95 note threshold."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import golden_inputs as gi
+import gpu_util
+from oracle import vae as ovae
+
+pytestmark = pytest.mark.gpu
+GOLD = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "vae.npz"))
+
+
+def test_decode_tiles_matches_reference(cuda):
+    vae, _ = gpu_util.native_vae(cuda)
+    out = vae.decode(gi.vae_tiles().to(cuda)).cpu()
+    ref = torch.from_numpy(GOLD["tiles"])
+    assert out.shape == ref.shape
+    err = gpu_util.rel_l2(out, ref)
+    flips = ((out >= -0.95) != (ref >= -0.95)).float().mean().item()
+    assert err < 5e-3, err
+    assert flips < 5e-3, flips
+
+
+def test_decode_latents_layout_and_chunking(cuda, monkeypatch):
+    """_decode's tile-major re-tiling: roll[b, :, :, k*128:(k+1)*128] is tile k of sample b; chunked == unchunked."""
+    vae, sd = gpu_util.native_vae(cuda)
+    lat = gi.vae_latents()
+    roll = vae.decode_latents(lat.to(cuda), gi.SCALE_FACTOR).cpu()
+    ref_sub = torch.from_numpy(GOLD["decode_latents_sub4"])
+    assert gpu_util.rel_l2(roll[:, :, ::4, ::4], ref_sub) < 5e-3
+    monkeypatch.setenv("RGM_VAE_CHUNK", "3")
+    vae2, _ = gpu_util.native_vae(cuda)
+    roll2 = vae2.decode_latents(lat.to(cuda), gi.SCALE_FACTOR).cpu()
+    assert torch.equal(roll, roll2)
+    ch0 = vae.decode_latents(lat.to(cuda), gi.SCALE_FACTOR, channels=1).cpu()
+    assert torch.equal(ch0[:, 0], roll[:, 0])
+
+
+def test_decode_many_tiles_vs_oracle(cuda):
+    """More tiles than one chunk, random latents, against the oracle run on the CPU here."""
+    vae, sd = gpu_util.native_vae(cuda)
+    g = torch.Generator(device="cpu").manual_seed(9)
+    lat = torch.randn(3, 4, 48, 16, generator=g)
+    with torch.no_grad():
+        ref = ovae.decode_latents(sd, lat, 1.3)
+    out = vae.decode_latents(lat.to(cuda), 1.3).cpu()
+    assert gpu_util.rel_l2(out, ref) < 5e-3

@@ -32,6 +32,12 @@ int rgm_version(void);
 unsigned long long rgm_launch_count(void);
 /* 0 when the current device is sm_100 (B200); negative with an error message otherwise */
 int rgm_check_device(void);
+/* Optional per-launch device timer used by bench.py for the roofline figures: while enabled, every kernel launch of the
+ * library is bracketed by CUDA events on its stream.  rgm_prof_enable(1) clears and starts, (0) stops.
+ * rgm_prof_summary synchronises the device and writes one line per kernel family into a HOST buffer:
+ * name \t launches \t total_ms \t flops_algorithmic \t flops_executed \t bytes_algorithmic */
+int rgm_prof_enable(int on);
+int rgm_prof_summary(char* buf_host, int cap);
 
 /* ---- denoiser: DiTRotary.forward (guided_diffusion/dit.py:538-634; registry DiT_models dit.py:969-983) -------- */
 typedef struct rgm_dit rgm_dit;

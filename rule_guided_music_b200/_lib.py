@@ -38,6 +38,8 @@ def _declare(lib):
 _HP = ctypes.POINTER(ctypes.c_void_p)
 c_char_p = ctypes.c_char_p
 _SIGNATURES = {
+    "rgm_prof_enable": [c_int],
+    "rgm_prof_summary": [c_char_p, c_int],
     "rgm_dit_create": [_HP, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int],
     "rgm_dit_destroy": [c_void_p],
     "rgm_dit_load": [c_void_p, c_char_p, c_void_p, c_ll, c_void_p],
@@ -98,6 +100,21 @@ def stream_ptr():
     import torch
 
     return c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def prof_enable(on):
+    call("rgm_prof_enable", 1 if on else 0)
+
+
+def prof_summary():
+    """Per kernel family: dict(name -> dict(launches, ms, flops_alg, flops_exec, bytes))."""
+    buf = ctypes.create_string_buffer(1 << 20)
+    call("rgm_prof_summary", buf, len(buf))
+    out = {}
+    for line in buf.value.decode().splitlines():
+        name, n, ms, fa, fe, by = line.split("\t")
+        out[name] = dict(launches=int(n), ms=float(ms), flops_alg=float(fa), flops_exec=float(fe), bytes=float(by))
+    return out
 
 
 def launch_count():

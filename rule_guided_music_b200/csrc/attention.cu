@@ -12,6 +12,7 @@
 #include <mutex>
 #include <unordered_map>
 
+#include "api_util.h"
 #include "aux_kernels.h"
 #include "ptx.cuh"
 
@@ -57,10 +58,13 @@ attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
   const uint32_t q_bytes = p.nkb * 16384u;           // per query tile: nkb blocks of [128 rows][128 B]
   const uint32_t k_blk = (uint32_t)T * 128u;         // one k-block of K: [T rows][128 B]
   const uint32_t v_blk = (uint32_t)p.npv * 128u;     // one 64-token block of V^T: [npv rows][128 B]
-  uint8_t* sQ = smem;                                // two query tiles
-  uint8_t* sK = sQ + 2 * q_bytes;
+  uint8_t* sQ = smem;                                // query tile 0 (tile 1 is staged in the P buffer, see below)
+  uint8_t* sK = sQ + q_bytes;
   uint8_t* sV = sK + p.nkb * k_blk;
   uint8_t* sP = sV + (T / 64) * v_blk;               // [T/64 blocks][128 rows][128 B]
+  // Query tile 1 lives at the start of the P buffer until S1 = Q1 K^T has completed: P0 is not written before that
+  // (the softmax warps wait on bar_s[1] first), so 227 KB of shared memory hold Q0, K, V^T and P.
+  uint8_t* sQ1 = sP;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sP + (T / 64) * 16384u);
   uint64_t* bar_load = bars;        // Q tiles + K + V landed
   uint64_t* bar_s = bars + 1;       // [2] S tile complete
@@ -109,7 +113,7 @@ attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
         const int row0 = pair * T;
         for (int kb = 0; kb < p.nkb; ++kb) {
           for (int m = 0; m < p.n_tiles; ++m)
-            tma_load_2d(sQ + m * q_bytes + kb * 16384, &map_q, bar_load, kb * 64, row0 + m * 128);
+            tma_load_2d((m ? sQ1 : sQ) + kb * 16384, &map_q, bar_load, kb * 64, row0 + m * 128);
           for (int j = 0; j < p.n_tiles; ++j)
             tma_load_2d(sK + kb * k_blk + j * 16384, &map_k, bar_load, kb * 64, row0 + j * 128);
         }
@@ -120,7 +124,7 @@ attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
         for (int m = 0; m < p.n_tiles; ++m) {
           for (int ks = 0; ks < p.ksteps; ++ks) {
             const int kb = ks >> 2, kk = ks & 3;
-            umma_f16(tmem_base + m * 256, umma_desc_sw128(sQ + m * q_bytes + kb * 16384) + 2 * kk,
+            umma_f16(tmem_base + m * 256, umma_desc_sw128((m ? sQ1 : sQ) + kb * 16384) + 2 * kk,
                      umma_desc_sw128(sK + kb * k_blk) + 2 * kk, idesc_s, ks != 0);
           }
           umma_commit(&bar_s[m]);
@@ -158,6 +162,7 @@ attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
         }
         // the single P buffer is read by the previous tile's P V MMAs: wait for them before overwriting it
         if (m > 0) mbar_wait(&bar_o[m - 1], ph);
+        else if (p.n_tiles > 1) mbar_wait(&bar_s[1], ph);  // Q1 is staged in the P buffer until S1 is done
         const float mneg = -mx * p.scale_log2e;
         float sum = 0.f;
         for (int c = 0; c < T; c += 32) {
@@ -279,18 +284,23 @@ cudaError_t launch_attention(const __half* q, const __half* k, const __half* vt,
   if (!map2d(&mq, q, dh, rows, 64, 128) || !map2d(&mk, k, dh, rows, 64, 128) ||
       !map2d(&mv, vt, T, (unsigned long long)B * heads * dh, 64, p.npv))
     return fail("attention: cuTensorMapEncodeTiled failed");
-  const size_t smem = 1024 + 2 * p.nkb * 16384 + (size_t)p.nkb * T * 128 + (size_t)(T / 64) * p.npv * 128 +
+  const size_t smem = 1024 + p.nkb * 16384 + (size_t)p.nkb * T * 128 + (size_t)(T / 64) * p.npv * 128 +
                       (size_t)(T / 64) * 16384 + 128;
   static size_t smem_set = 0;
   if (smem > smem_set) {
     cudaError_t e = cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
+    if (e != cudaSuccess) {
+      if (err) *err = std::string("attention: cudaFuncSetAttribute(shared memory): ") + cudaGetErrorString(e);
+      return e;
+    }
     smem_set = smem;
   }
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int grid = p.n_pairs < sms ? p.n_pairs : sms;
+  const double fl = 4.0 * (double)B * heads * T * T * dh;
+  ProfScope prof("attention", fl, 4.0 * (double)B * heads * T * T * p.npv, 0.0, s);
   attention_kernel<<<grid, ATT_THREADS, smem, s>>>(mq, mk, mv, p);
   g_att_launches.fetch_add(1, std::memory_order_relaxed);
   cudaError_t st = cudaGetLastError();

@@ -3,6 +3,7 @@
 // consecutive addresses, with grids sized from the row count (these are all HBM-bound).
 #include <atomic>
 
+#include "api_util.h"
 #include "aux_kernels.h"
 #include "ptx.cuh"
 
@@ -141,6 +142,7 @@ __global__ void __launch_bounds__(256) ln_modulate_kernel(const float* __restric
 cudaError_t launch_ln_modulate(const float* x, const float* shift, const float* scale, int mod_ld, __half* out,
                                long long rows, int D, int rows_per_sample, float eps, cudaStream_t s) {
   const int grid = blocks_for(rows, 8, 148 * 8);
+  ProfScope prof("ln_modulate", 0, 0, (double)rows * D * 6.0, s);
 #define RGM_LN(NV)                                                                                                   \
   case NV:                                                                                                           \
     ln_modulate_kernel<NV><<<grid, 256, 0, s>>>(x, shift, scale, mod_ld, out, rows, rows_per_sample, eps);           \
@@ -226,6 +228,7 @@ cudaError_t launch_vae_stem(const float* lat, float scale, const float* pq_w, co
                             const float* cin_w, const float* cin_b, __half* out, int n_cand, int Hlat, int tile0,
                             int n_tiles, int Cout, cudaStream_t s) {
   if (Cout % 64 != 0 || n_tiles <= 0) return cudaErrorInvalidValue;
+  ProfScope prof("vae_stem", 0, 0, (double)n_tiles * 256.0 * (Cout * 2.0 + 16.0), s);
   vae_stem_kernel<<<n_tiles, 256, 0, s>>>(lat, scale, pq_w, pq_b, cin_w, cin_b, out, n_cand, Hlat, tile0, Cout);
   return done();
 }
@@ -270,6 +273,7 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(const __half* __restrict_
 cudaError_t launch_gn_stats(const __half* x, const float* gamma, const float* beta, float2* ab, int n, int HW, int C,
                             float eps, cudaStream_t s) {
   if (C % 32 != 0) return cudaErrorInvalidValue;
+  ProfScope prof("gn_stats", 0, 0, (double)n * HW * C * 2.0, s);
   gn_stats_kernel<<<dim3(32, n), 256, 0, s>>>(x, gamma, beta, ab, HW, C, eps);
   return done();
 }
@@ -323,6 +327,7 @@ cudaError_t launch_gn_finalize(const float* part, const float* gamma, const floa
                                int slots_per_img, int n_par, long long par_stride, int C, int HW_out, float eps,
                                cudaStream_t s) {
   if (C % 128 != 0) return cudaErrorInvalidValue;
+  ProfScope prof("gn_finalize", 0, 0, (double)n * n_par * slots_per_img * (C / 4) * 8.0, s);
   gn_finalize_kernel<<<dim3(32, n), 128, 0, s>>>(part, gamma, beta, ab, slots_per_img, n_par, par_stride, C, HW_out,
                                                  eps);
   return done();
@@ -361,6 +366,7 @@ cudaError_t launch_gn_apply(const __half* x, const float2* ab, __half* y, int n,
                             cudaStream_t s) {
   if (C % 8 != 0) return cudaErrorInvalidValue;
   const long long total_vec = (long long)n * HW * (C / 8);
+  ProfScope prof("gn_apply", 0, 0, (double)total_vec * 32.0, s);
   gn_apply_kernel<<<blocks_for(total_vec, 256 * 4, 148 * 16), 256, 0, s>>>(x, ab, y, total_vec, HW, C, swish);
   return done();
 }
@@ -402,6 +408,7 @@ __global__ void __launch_bounds__(256) softmax_rows_kernel(const float* __restri
 
 cudaError_t launch_softmax_rows(const float* x, __half* y, long long rows, int cols, cudaStream_t s) {
   if (cols % 32 != 0 || cols > 1024) return cudaErrorInvalidValue;
+  ProfScope prof("softmax_rows", 0, 0, (double)rows * cols * 6.0, s);
   softmax_rows_kernel<<<blocks_for(rows, 8, 148 * 8), 256, 0, s>>>(x, y, rows, cols);
   return done();
 }
@@ -419,6 +426,7 @@ __global__ void transpose_kernel(const __half* __restrict__ x, __half* __restric
 
 cudaError_t launch_transpose(const __half* x, __half* y, int n, int R, int C, cudaStream_t s) {
   if (R % 32 != 0 || C % 32 != 0) return cudaErrorInvalidValue;
+  ProfScope prof("transpose", 0, 0, (double)n * R * C * 4.0, s);
   transpose_kernel<<<dim3(C / 32, R / 32, n), dim3(32, 8), 0, s>>>(x, y, R, C);
   return done();
 }

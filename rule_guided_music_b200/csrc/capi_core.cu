@@ -1,7 +1,11 @@
 // C ABI: library-level entry points and the GEMM / convolution building blocks (include/rgm_b200.h).
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
+#include <map>
+#include <mutex>
 #include <string>
+#include <vector>
 
 #include "../../include/rgm_b200.h"
 #include "api_util.h"
@@ -22,6 +26,31 @@ int check_cuda(cudaError_t e, const char* what) {
 }
 
 std::atomic<unsigned long long> g_aux_launches{0};
+
+// ---- optional per-launch timer (rgm_prof_*) -------------------------------------------------------------------
+std::atomic<int> g_prof_on{0};
+namespace {
+struct ProfRec {
+  std::string name;
+  double flops_alg, flops_exec, bytes;
+  cudaEvent_t e0, e1;
+};
+std::mutex g_prof_mu;
+std::vector<ProfRec> g_prof;
+}  // namespace
+
+void prof_open(const char* name, double flops_alg, double flops_exec, double bytes, cudaStream_t st) {
+  ProfRec r{name, flops_alg, flops_exec, bytes, nullptr, nullptr};
+  cudaEventCreate(&r.e0);
+  cudaEventCreate(&r.e1);
+  cudaEventRecord(r.e0, st);
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  g_prof.push_back(r);
+}
+void prof_close(cudaStream_t st) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  if (!g_prof.empty()) cudaEventRecord(g_prof.back().e1, st);
+}
 
 // weight fp32 [Cout,Cin,kh,kw] -> packed fp16 [rows][taps*cin_pad]
 __global__ void pack_conv_weight_kernel(const float* __restrict__ w, __half* __restrict__ out, int Cout, int Cin,
@@ -77,6 +106,50 @@ int rgm_version(void) { return 100; }
 unsigned long long rgm_launch_count(void) {
   return gemm_launch_count() + g_aux_launches.load() + aux_launch_count() + attention_launch_count() +
          rules_launch_count();
+}
+
+int rgm_prof_enable(int on) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  for (auto& r : g_prof) {
+    cudaEventDestroy(r.e0);
+    cudaEventDestroy(r.e1);
+  }
+  g_prof.clear();
+  g_prof_on.store(on ? 1 : 0);
+  return 0;
+}
+
+int rgm_prof_summary(char* buf_host, int cap) {
+  if (!buf_host || cap <= 0) return set_error("rgm_prof_summary: bad buffer");
+  if (cudaDeviceSynchronize() != cudaSuccess) return set_error("rgm_prof_summary: device error");
+  struct Agg {
+    long long n = 0;
+    double ms = 0, fa = 0, fe = 0, by = 0;
+  };
+  std::map<std::string, Agg> agg;
+  {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    for (auto& r : g_prof) {
+      float ms = 0.f;
+      if (cudaEventElapsedTime(&ms, r.e0, r.e1) != cudaSuccess) continue;
+      Agg& a = agg[r.name];
+      a.n++;
+      a.ms += ms;
+      a.fa += r.flops_alg;
+      a.fe += r.flops_exec;
+      a.by += r.bytes;
+    }
+  }
+  std::string out;
+  char line[512];
+  for (auto& kv : agg) {
+    snprintf(line, sizeof line, "%s\t%lld\t%.6f\t%.6e\t%.6e\t%.6e\n", kv.first.c_str(), kv.second.n, kv.second.ms,
+             kv.second.fa, kv.second.fe, kv.second.by);
+    out += line;
+  }
+  if ((int)out.size() + 1 > cap) return set_error("rgm_prof_summary: buffer too small");
+  memcpy(buf_host, out.c_str(), out.size() + 1);
+  return 0;
 }
 
 int rgm_check_device(void) {

@@ -5,6 +5,7 @@
 #include <mutex>
 #include <unordered_map>
 
+#include "api_util.h"
 #include "gemm_host.h"
 
 namespace rgm {
@@ -210,6 +211,17 @@ cudaError_t launch_gemm(const GemmDesc& d, cudaStream_t stream, std::string* err
   const long long total = (long long)p.num_m_tiles * p.num_n_tiles * p.num_par;
   const int grid = (int)(total < device_sm_count() ? total : device_sm_count());
   if (grid <= 0) return cudaSuccess;
+
+  // profiling label: conv kind, K, N and epilogue identify the layer family; flops_alg counts the reference's
+  // arithmetic (a 3x3 conv on the upsampled image for CONV_UP2), flops_exec what this kernel executes
+  char pname[96];
+  const double Kexec = (double)p.num_taps * d.C;
+  const double rows = (double)p.M * p.num_par;
+  const double f_exec = 2.0 * rows * d.N * Kexec;
+  const double f_alg = d.conv == CONV_UP2 ? 2.0 * rows * d.N * 9.0 * d.C : f_exec;
+  if (g_prof_on.load(std::memory_order_relaxed))
+    snprintf(pname, sizeof pname, "gemm_tc conv%d K%d N%d epi%d bn%d", d.conv, (int)Kexec, d.N, d.epi, bn);
+  ProfScope prof(pname, f_alg, f_exec, 0.0, stream);
 
   cudaError_t st = cudaErrorInvalidValue;
 #define RGM_CASE(BN, EPI)                                              \

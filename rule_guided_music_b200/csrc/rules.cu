@@ -7,6 +7,7 @@
 // rule sees what an earlier rule left behind; thresholds and counts are exact integer work, the histogram is fp32.
 #include <atomic>
 
+#include "api_util.h"
 #include "aux_kernels.h"
 
 namespace rgm {
@@ -59,6 +60,7 @@ __global__ void __launch_bounds__(256) pitch_hist_kernel(float* __restrict__ rol
 
 cudaError_t launch_rule_pitch_hist(float* roll, float* hist, int n, int ch, int L, cudaStream_t s) {
   if (L % 4 != 0 || n <= 0) return cudaErrorInvalidValue;
+  ProfScope prof("rule_pitch_hist", 0, 0, (double)n * 128.0 * L * 4.0, s);
   pitch_hist_kernel<<<n, 256, 0, s>>>(roll, hist, ch, L);
   return done();
 }
@@ -142,6 +144,7 @@ cudaError_t launch_rule_note_density(float* roll, float* out, int n, int ch, int
   if (interval >= 128 && (interval % 128) != 0) return cudaErrorInvalidValue;
   const int nwin = L / interval;
   const long long total = (long long)n * 2 * nwin;
+  ProfScope prof("rule_note_density", 0, 0, (double)n * 128.0 * L * 8.0, s);
   cudaError_t e = cudaMemsetAsync(out, 0, total * sizeof(float), s);
   if (e != cudaSuccess) return e;
   note_density_kernel<<<dim3(L / 128, n), 128, 0, s>>>(roll, out, ch, L, interval, hscale);

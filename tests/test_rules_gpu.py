@@ -67,14 +67,16 @@ def test_loss_accum_and_select(cuda):
     gen = torch.rand(N * B, K, generator=g)
     tgt = torch.rand(B, K, generator=g)
     total = torch.zeros(N * B, device=cuda)
-    _lib.call("rgm_rule_loss_accum", _lib.ptr(gen.to(cuda)), _lib.ptr(tgt.to(cuda)), _lib.ptr(total), N * B, B, K, 0,
+    gen_d, tgt_d = gen.to(cuda), tgt.to(cuda)  # keep the device tensors alive across the asynchronous call
+    _lib.call("rgm_rule_loss_accum", _lib.ptr(gen_d), _lib.ptr(tgt_d), _lib.ptr(total), N * B, B, K, 0,
               0.7, _lib.stream_ptr())
     ref = -orules.LOSS_DICT["pitch_hist"](gen, tgt.repeat(N, 1)) * 0.7
     assert torch.allclose(total.cpu(), ref, rtol=1e-6, atol=1e-8)
     gi_ = torch.randint(0, 3, (N * B, K), generator=g).float()
     ti_ = torch.randint(0, 3, (B, K), generator=g).float()
     tot2 = torch.zeros(N * B, device=cuda)
-    _lib.call("rgm_rule_loss_accum", _lib.ptr(gi_.to(cuda)), _lib.ptr(ti_.to(cuda)), _lib.ptr(tot2), N * B, B, K, 1,
+    gi_d, ti_d = gi_.to(cuda), ti_.to(cuda)
+    _lib.call("rgm_rule_loss_accum", _lib.ptr(gi_d), _lib.ptr(ti_d), _lib.ptr(tot2), N * B, B, K, 1,
               1.0, _lib.stream_ptr())
     assert torch.equal(tot2.cpu(), -orules.LOSS_DICT["note_density_class"](gi_, ti_.repeat(N, 1)))
     assert LOSS_DICT["pitch_hist"] is not None
@@ -88,7 +90,8 @@ def test_select_first_max_with_ties(cuda, N, B, elems):
     cand = torch.randn(N, B, elems, generator=g)
     out = torch.empty(B, elems, device=cuda)
     idx = torch.empty(B, dtype=torch.int64, device=cuda)
-    _lib.call("rgm_scg_select", _lib.ptr(total.to(cuda)), _lib.ptr(cand.to(cuda)), _lib.ptr(out), _lib.ptr(idx), N, B,
+    total_d, cand_d = total.to(cuda), cand.to(cuda)
+    _lib.call("rgm_scg_select", _lib.ptr(total_d), _lib.ptr(cand_d), _lib.ptr(out), _lib.ptr(idx), N, B,
               elems, _lib.stream_ptr())
     ref_idx = total.argmax(dim=0)
     assert torch.equal(idx.cpu(), ref_idx)

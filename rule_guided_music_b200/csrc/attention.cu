@@ -179,10 +179,10 @@ attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
             h2[i >> 1] = __floats2half2_rn(e0, e1);
           }
           // columns c..c+31 = 16-byte chunks (c%64)/8 .. +3 of row r in token block c/64, 128-byte swizzle
-          uint8_t* rowp = sP + (c >> 6) * 16384 + r * 128;
+          const uint32_t rowp = smem_u32(sP) + (c >> 6) * 16384 + r * 128;
           const int ch0 = (c & 63) >> 3;
 #pragma unroll
-          for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(rowp + (((ch0 + j) ^ (r & 7)) << 4)) = pk[j];
+          for (int j = 0; j < 4; ++j) sts_v4(rowp + (((ch0 + j) ^ (r & 7)) << 4), pk[j]);
         }
         inv_sum[m] = 1.0f / sum;
         tc_fence_before();

@@ -193,6 +193,7 @@ int rgm_gemm_f16(const void* a16, const void* b16, const float* bias, float* out
   d.e.bias = bias;
   d.e.alpha = 1.f;
   if (getenv("RGM_DEBUG_SKIP_STORE")) d.e.act = 99;  // development knob (see gemm_tc.cuh)
+  if (const char* tr = getenv("RGM_DEBUG_TRACE_PTR")) d.trace = reinterpret_cast<unsigned long long*>(strtoull(tr, nullptr, 0));
   std::string err;
   if (launch_gemm(d, static_cast<cudaStream_t>(stream), &err) != cudaSuccess) return set_error(err);
   return 0;
@@ -221,6 +222,7 @@ int rgm_conv_f16(const void* x16, const void* w16_packed, const float* bias, con
   d.e.resid = static_cast<const __half*>(resid16);
   d.e.ldr = Cout;
   d.e.gn_part = gn_part;
+  if (const char* tr = getenv("RGM_DEBUG_TRACE_PTR")) d.trace = reinterpret_cast<unsigned long long*>(strtoull(tr, nullptr, 0));
   if (kind == CONV_UP2) {
     d.e.up2 = 1;
     d.e.upH = H;

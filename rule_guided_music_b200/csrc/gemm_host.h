@@ -27,6 +27,7 @@ struct GemmDesc {
   int conv = CONV_1x1;
   int epi = EPI_F16;
   int block_n = 0;    // 0 = choose
+  unsigned long long* trace = nullptr;  // development aid, see GemmParams::trace
   EpiParams e{};
 };
 

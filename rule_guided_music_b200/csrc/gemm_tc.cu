@@ -98,18 +98,18 @@ bool make_map(CUtensorMap* out, const void* ptr, int rank, const cuuint64_t* dim
 
 std::atomic<unsigned long long> g_launches{0};
 
-template <int BN, int EPI>
+template <int BN, int MT, int EPI>
 cudaError_t launch_inst(const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& p, int grid,
                         cudaStream_t stream) {
   static bool attr_set = false;
-  auto kern = gemm_tc_kernel<BN, EPI>;
+  auto kern = gemm_tc_kernel<BN, MT, EPI>;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)GemmCfg<BN>::SMEM_BYTES);
+                                         (int)GemmCfg<BN, MT>::SMEM_BYTES);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  kern<<<grid, GEMM_THREADS, GemmCfg<BN>::SMEM_BYTES, stream>>>(ma, mb, p);
+  kern<<<grid, GEMM_THREADS, GemmCfg<BN, MT>::SMEM_BYTES, stream>>>(ma, mb, p);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return cudaGetLastError();
 }
@@ -179,6 +179,7 @@ cudaError_t launch_gemm(const GemmDesc& d, cudaStream_t stream, std::string* err
     return fail("gemm: unknown conv kind");
   }
   p.epi = d.e;
+  p.trace = d.trace;
 
   int bn = d.block_n;
   if (bn == 0) {
@@ -208,7 +209,15 @@ cudaError_t launch_gemm(const GemmDesc& d, cudaStream_t stream, std::string* err
     if (!make_map(&mb, d.B, 3, dims, strides, box, err)) return cudaErrorInvalidValue;
   }
 
-  const long long total = (long long)p.num_m_tiles * p.num_n_tiles * p.num_par;
+  // narrow outputs (N tile 128) process two 128-row sub-tiles per tile so the B stage is shared (see GemmCfg)
+  int mt = 1;
+  if (bn == 128 && (long long)(p.num_m_tiles / 2) * p.num_n_tiles * p.num_par >= device_sm_count()) mt = 2;
+  if (d.epi == EPI_QKV_ROPE && (d.e.T % 32 != 0 || (d.e.heads * d.e.dh) % 32 != 0))
+    return fail("gemm: the QKV epilogue needs T and hidden to be multiples of 32");
+  if (d.epi == EPI_GATE_RESID && d.e.rows_per_sample % 32 != 0)
+    return fail("gemm: the gate/residual epilogue needs rows_per_sample to be a multiple of 32");
+  if ((long long)p.M * (d.conv == CONV_UP2 ? 4 : 1) >= (1LL << 31)) return fail("gemm: more than 2^31 output rows");
+  const long long total = (long long)((p.num_m_tiles + mt - 1) / mt) * p.num_n_tiles * p.num_par;
   const int grid = (int)(total < device_sm_count() ? total : device_sm_count());
   if (grid <= 0) return cudaSuccess;
 
@@ -220,27 +229,31 @@ cudaError_t launch_gemm(const GemmDesc& d, cudaStream_t stream, std::string* err
   const double f_exec = 2.0 * rows * d.N * Kexec;
   const double f_alg = d.conv == CONV_UP2 ? 2.0 * rows * d.N * 9.0 * d.C : f_exec;
   if (g_prof_on.load(std::memory_order_relaxed))
-    snprintf(pname, sizeof pname, "gemm_tc conv%d K%d N%d epi%d bn%d", d.conv, (int)Kexec, d.N, d.epi, bn);
+    snprintf(pname, sizeof pname, "gemm_tc conv%d K%d N%d epi%d bn%dx%d", d.conv, (int)Kexec, d.N, d.epi, bn, mt);
   ProfScope prof(pname, f_alg, f_exec, 0.0, stream);
 
   cudaError_t st = cudaErrorInvalidValue;
-#define RGM_CASE(BN, EPI)                                              \
-  if (bn == BN && d.epi == EPI) {                                      \
-    st = launch_inst<BN, EPI>(ma, mb, p, grid, stream);                \
+#define RGM_CASE(BN, MT, EPI)                                          \
+  if (bn == BN && mt == MT && d.epi == EPI) {                          \
+    st = launch_inst<BN, MT, EPI>(ma, mb, p, grid, stream);            \
     goto done;                                                         \
   }
-  RGM_CASE(256, EPI_F16)
-  RGM_CASE(128, EPI_F16)
-  RGM_CASE(32, EPI_F16)
-  RGM_CASE(256, EPI_F32)
-  RGM_CASE(128, EPI_F32)
-  RGM_CASE(32, EPI_F32)
-  RGM_CASE(256, EPI_GATE_RESID)
-  RGM_CASE(128, EPI_GATE_RESID)
-  RGM_CASE(256, EPI_QKV_ROPE)
-  RGM_CASE(128, EPI_QKV_ROPE)
-  RGM_CASE(32, EPI_UNPATCH)
-  RGM_CASE(32, EPI_ROLL)
+  RGM_CASE(256, 1, EPI_F16)
+  RGM_CASE(128, 2, EPI_F16)
+  RGM_CASE(128, 1, EPI_F16)
+  RGM_CASE(32, 1, EPI_F16)
+  RGM_CASE(256, 1, EPI_F32)
+  RGM_CASE(128, 2, EPI_F32)
+  RGM_CASE(128, 1, EPI_F32)
+  RGM_CASE(32, 1, EPI_F32)
+  RGM_CASE(256, 1, EPI_GATE_RESID)
+  RGM_CASE(128, 2, EPI_GATE_RESID)
+  RGM_CASE(128, 1, EPI_GATE_RESID)
+  RGM_CASE(256, 1, EPI_QKV_ROPE)
+  RGM_CASE(128, 2, EPI_QKV_ROPE)
+  RGM_CASE(128, 1, EPI_QKV_ROPE)
+  RGM_CASE(32, 1, EPI_UNPATCH)
+  RGM_CASE(32, 1, EPI_ROLL)
 #undef RGM_CASE
   return fail("gemm: no kernel instance for this (N tile, epilogue)");
 done:

@@ -65,219 +65,280 @@ struct GemmParams {
   int b_batched;              // B's third coordinate follows the image index (batched GEMM)
   signed char tap_dy[4][9];
   signed char tap_dx[4][9];
+  // development aid: when non-null, CTA 0 writes clock64() at pipeline events of each of its tiles, 8 slots per tile:
+  // 0 producer tile start, 1 MMA accumulator free, 2 MMA first operands landed, 3 MMA last issue,
+  // 4 epilogue accumulator ready, 5 epilogue done
+  unsigned long long* trace;
   EpiParams epi;
 };
 
-constexpr int GEMM_BLOCK_M = 128;
+constexpr int GEMM_BLOCK_M = 128;   // rows of one UMMA (and of one TMA box of A)
 constexpr int GEMM_BLOCK_K = 64;
-constexpr int GEMM_THREADS = 192;
+constexpr int GEMM_EPI_WARPS = 8;
+constexpr int GEMM_THREADS = 64 + 32 * GEMM_EPI_WARPS;  // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
 
-template <int BLOCK_N>
+// BLOCK_N: output columns per tile; MT: 128-row sub-tiles per tile (the B stage is shared by the MT UMMAs, which
+// halves L2->smem operand traffic per flop for narrow outputs such as the 128-channel convolutions).
+template <int BLOCK_N, int MT>
 struct GemmCfg {
-  static constexpr int STAGES = (BLOCK_N == 256) ? 4 : (BLOCK_N == 128 ? 6 : 8);
-  static constexpr uint32_t A_BYTES = GEMM_BLOCK_M * GEMM_BLOCK_K * 2;
+  static constexpr uint32_t A_BYTES = MT * GEMM_BLOCK_M * GEMM_BLOCK_K * 2;
   static constexpr uint32_t B_BYTES = BLOCK_N * GEMM_BLOCK_K * 2;
-  static constexpr uint32_t TMEM_COLS = (2 * BLOCK_N < 32) ? 32 : 2 * BLOCK_N;
-  static constexpr size_t SMEM_BYTES = 1024 /*align slack*/ + STAGES * (A_BYTES + B_BYTES) + 256 /*barriers*/;
+  static constexpr uint32_t STAGE_BYTES_EPI = GEMM_EPI_WARPS * 32 * 32 * 4;  // per-warp transpose staging
+  static constexpr int STAGES = (A_BYTES + B_BYTES) >= 49152 ? 4 : ((A_BYTES + B_BYTES) >= 32768 ? 6 : 8);
+  static constexpr uint32_t ACC_COLS = MT * BLOCK_N;                  // TMEM columns of one accumulator buffer
+  static constexpr uint32_t TMEM_COLS = (2 * ACC_COLS < 32) ? 32 : 2 * ACC_COLS;
+  static constexpr size_t SMEM_BYTES =
+      1024 /*align slack*/ + STAGES * (A_BYTES + B_BYTES) + STAGE_BYTES_EPI + 256 /*barriers*/;
+  static_assert(TMEM_COLS <= 512, "accumulators do not fit tensor memory");
+  static_assert(SMEM_BYTES <= 232448, "shared memory budget");
 };
 
 // ------------------------------------------------------------------------------------------------
-// epilogue: one thread owns one output row and 32 consecutive columns of it
+// epilogue
+//
+// An epilogue warp owns 32 accumulator rows (its TMEM lane quadrant) and walks its share of the columns in rounds
+// of 32.  tcgen05.ld hands thread i row i of the round; most epilogues then transpose the 32x32 block through a
+// warp-private, XOR-swizzled shared-memory tile so that thread i owns COLUMN n0+i instead: global loads and stores
+// of a row then cover 64 (fp16) or 128 (fp32) contiguous bytes per instruction, per-column constants (bias, gate)
+// are one register, and GroupNorm column sums need two shuffles.  The scatter epilogues whose destination is
+// contiguous along rows (V^T, the piano roll, the latent) keep the row-per-thread orientation.
 // ------------------------------------------------------------------------------------------------
-template <int EPI>
-__device__ __forceinline__ void epilogue_chunk(const GemmParams& p, int row, int n0, int par, const uint32_t (&r)[32]) {
-  const EpiParams& e = p.epi;
-  const bool row_ok = row < p.M;
-  float v[32];
-#pragma unroll
-  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+template <int ACT>
+__device__ __forceinline__ float apply_act(float x) {
+  if constexpr (ACT == ACT_SILU) return silu_f(x);
+  else if constexpr (ACT == ACT_GELU_TANH) return gelu_tanh_f(x);
+  else return x;
+}
 
-  if constexpr (EPI == EPI_F16 || EPI == EPI_F32) {
-    const float* addrow = nullptr;
-    if (e.addtab != nullptr && row_ok) addrow = e.addtab + e.addidx[row] * (long long)p.N;
+// Fast column loops: the 32 rows of the round are all valid and their destination rows are equally spaced
+// (`ostride` elements apart), so addresses advance by pointer increments -- about ten instructions per element.
+template <int ACT, bool RESID>
+__device__ __forceinline__ void cols_f16_fast(const float (&val)[32], __half* op, const __half* rp, long long ostride,
+                                              long long rstride, float alpha, float bias, float& s, float& q) {
 #pragma unroll
-    for (int i = 0; i < 32; ++i) {
-      float x = v[i] * e.alpha;
-      if (e.bias) x += __ldg(e.bias + n0 + i);
-      if (addrow) x += __ldg(addrow + n0 + i);
-      if (e.act == ACT_SILU) x = silu_f(x);
-      else if (e.act == ACT_GELU_TANH) x = gelu_tanh_f(x);
-      v[i] = x;
+  for (int j = 0; j < 32; ++j) {
+    float x = apply_act<ACT>(fmaf(val[j], alpha, bias));
+    if constexpr (RESID) {
+      x += __half2float(*rp);
+      rp += rstride;
     }
-    long long orow = row;
-    if (e.up2) {
-      const int hw = e.upH * e.upW;
-      const int img = row / hw, rem = row - img * hw;
-      const int h = rem / e.upW, w = rem - h * e.upW;
-      orow = ((long long)img * (2 * e.upH) + (2 * h + (par >> 1))) * (2 * e.upW) + (2 * w + (par & 1));
-    }
-    if constexpr (EPI == EPI_F32) {
-      if (row_ok && e.act != 99) {  // act 99: development knob, skip the store
-        float4* dst = reinterpret_cast<float4*>(static_cast<float*>(e.out) + orow * e.ldo + n0);
+    const __half h = __float2half_rn(x);
+    *op = h;
+    op += ostride;
+    const float f = __half2float(h);  // statistics of exactly the value the next layer reads
+    s += f;
+    q = fmaf(f, f, q);
+  }
+}
+
+template <int EPI>
+__device__ __forceinline__ void epilogue_round_cols(const GemmParams& p, uint32_t stage, const uint32_t (&r)[32],
+                                                    int lane, int row0, int orow_lane, bool uniform_rows,
+                                                    int orow0, int orow_step, int n0, int par) {
+  const EpiParams& e = p.epi;
+  // transpose: thread `lane` (a row) writes its 32 values; afterwards thread `lane` (a column) reads 32 rows.
+  // `stage` is the shared-space address of this warp's 32x32 fp32 tile; element (row, col) lives at
+  // row*32 + (col ^ row): conflict-free for both the row-wise writes and the column-wise reads.
 #pragma unroll
-        for (int i = 0; i < 8; ++i) dst[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+  for (int c = 0; c < 32; ++c) sts_f32(stage + 4u * (lane * 32 + (c ^ lane)), __uint_as_float(r[c]));
+  __syncwarp();
+  float val[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) val[j] = lds_f32(stage + 4u * (j * 32 + (lane ^ j)));
+  const int n = n0 + lane;
+  const float bias = e.bias ? __ldg(e.bias + n) : 0.f;
+
+  if constexpr (EPI == EPI_F16) {
+    float s = 0.f, q = 0.f;
+    if (uniform_rows && e.addtab == nullptr) {
+      __half* op = static_cast<__half*>(e.out) + (long long)orow0 * e.ldo + n;
+      const long long ostride = (long long)orow_step * e.ldo;
+      if (e.resid != nullptr) {
+        const __half* rp = e.resid + (long long)orow0 * e.ldr + n;
+        const long long rstride = (long long)orow_step * e.ldr;
+        if (e.act == ACT_NONE) cols_f16_fast<ACT_NONE, true>(val, op, rp, ostride, rstride, e.alpha, bias, s, q);
+        else if (e.act == ACT_SILU) cols_f16_fast<ACT_SILU, true>(val, op, rp, ostride, rstride, e.alpha, bias, s, q);
+        else cols_f16_fast<ACT_GELU_TANH, true>(val, op, rp, ostride, rstride, e.alpha, bias, s, q);
+      } else {
+        if (e.act == ACT_NONE) cols_f16_fast<ACT_NONE, false>(val, op, nullptr, ostride, 0, e.alpha, bias, s, q);
+        else if (e.act == ACT_SILU) cols_f16_fast<ACT_SILU, false>(val, op, nullptr, ostride, 0, e.alpha, bias, s, q);
+        else cols_f16_fast<ACT_GELU_TANH, false>(val, op, nullptr, ostride, 0, e.alpha, bias, s, q);
       }
     } else {
-      if (e.resid != nullptr && row_ok) {
-        const uint4* rs = reinterpret_cast<const uint4*>(e.resid + orow * e.ldr + n0);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const uint4 u = __ldg(rs + i);
-          const __half2* h2 = reinterpret_cast<const __half2*>(&u);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float2 f = __half22float2(h2[j]);
-            v[8 * i + 2 * j] += f.x;
-            v[8 * i + 2 * j + 1] += f.y;
-          }
+      // general path: ragged last rows, 16-pixel-wide upsample rows, gathered row-vector add
+#pragma unroll 4
+      for (int j = 0; j < 32; ++j) {
+        const int orow = __shfl_sync(0xffffffffu, orow_lane, j);
+        float x = lds_f32(stage + 4u * (j * 32 + (lane ^ j))) * e.alpha + bias;
+        if (orow >= 0) {
+          if (e.addtab) x += __ldg(e.addtab + e.addidx[row0 + j] * (long long)p.N + n);
+          if (e.act == ACT_SILU) x = silu_f(x);
+          else if (e.act == ACT_GELU_TANH) x = gelu_tanh_f(x);
+          if (e.resid) x += __half2float(e.resid[(long long)orow * e.ldr + n]);
+          const __half h = __float2half_rn(x);
+          static_cast<__half*>(e.out)[(long long)orow * e.ldo + n] = h;
+          const float f = __half2float(h);
+          s += f;
+          q += f * f;
         }
       }
-      uint4 packed[4];
-      __half2* h2 = reinterpret_cast<__half2*>(packed);
-#pragma unroll
-      for (int i = 0; i < 16; ++i) h2[i] = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
-      if (row_ok) {
-        uint4* dst = reinterpret_cast<uint4*>(static_cast<__half*>(e.out) + orow * e.ldo + n0);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) dst[i] = packed[i];
+    }
+    if (e.gn_part != nullptr) {
+      // GroupNorm partials per (32 rows x 4 channels), no atomics (deterministic): lanes 4k..4k+3 hold one quad
+      s += __shfl_xor_sync(0xffffffffu, s, 1);
+      q += __shfl_xor_sync(0xffffffffu, q, 1);
+      s += __shfl_xor_sync(0xffffffffu, s, 2);
+      q += __shfl_xor_sync(0xffffffffu, q, 2);
+      if ((lane & 3) == 0) {
+        const long long slot = (long long)par * (p.num_m_tiles * 4) + (row0 >> 5);
+        reinterpret_cast<float2*>(e.gn_part)[slot * (p.N >> 2) + (n >> 2)] = make_float2(s, q);
       }
-      if (e.gn_part != nullptr) {
-        // GroupNorm partial statistics of exactly the values the next layer reads (fp16-rounded), without
-        // atomics so the result is run-to-run deterministic: this warp's 32 rows x 32 columns become 8
-        // (sum, sumsq) pairs, one per 4-channel quad; gn_finalize_kernel folds quads into groups and sums the
-        // per-warp slots of an image in a fixed order.
-        float s4[8], q4[8];
+    }
+  } else if constexpr (EPI == EPI_F32) {
+    if (uniform_rows && e.addtab == nullptr && e.act == ACT_NONE) {
+      float* op = static_cast<float*>(e.out) + (long long)orow0 * e.ldo + n;
+      const long long ostride = (long long)orow_step * e.ldo;
 #pragma unroll
-        for (int g = 0; g < 8; ++g) {
-          float s = 0.f, q = 0.f;
-#pragma unroll
-          for (int i = 0; i < 2; ++i) {
-            const float2 f = __half22float2(h2[2 * g + i]);
-            s += f.x + f.y;
-            q += f.x * f.x + f.y * f.y;
-          }
-          s4[g] = row_ok ? s : 0.f;
-          q4[g] = row_ok ? q : 0.f;
-        }
-#pragma unroll
-        for (int g = 0; g < 8; ++g) {
-#pragma unroll
-          for (int o = 16; o > 0; o >>= 1) {
-            s4[g] += __shfl_xor_sync(0xffffffffu, s4[g], o);
-            q4[g] += __shfl_xor_sync(0xffffffffu, q4[g], o);
-          }
-        }
-        if ((threadIdx.x & 31) == 0) {
-          const long long slot = (long long)par * (p.num_m_tiles * 4) + (row >> 5);
-          float2* dst = reinterpret_cast<float2*>(e.gn_part) + slot * (p.N >> 2) + (n0 >> 2);
-#pragma unroll
-          for (int g = 0; g < 8; ++g) dst[g] = make_float2(s4[g], q4[g]);
+      for (int j = 0; j < 32; ++j) {
+        *op = fmaf(val[j], e.alpha, bias);
+        op += ostride;
+      }
+    } else {
+#pragma unroll 4
+      for (int j = 0; j < 32; ++j) {
+        const int orow = __shfl_sync(0xffffffffu, orow_lane, j);
+        float x = lds_f32(stage + 4u * (j * 32 + (lane ^ j))) * e.alpha + bias;
+        if (orow >= 0) {
+          if (e.addtab) x += __ldg(e.addtab + e.addidx[row0 + j] * (long long)p.N + n);
+          if (e.act == ACT_SILU) x = silu_f(x);
+          else if (e.act == ACT_GELU_TANH) x = gelu_tanh_f(x);
+          static_cast<float*>(e.out)[(long long)orow * e.ldo + n] = x;
         }
       }
     }
   } else if constexpr (EPI == EPI_GATE_RESID) {
-    if (row_ok) {
-      const float* g = e.gate + (long long)(row / e.rows_per_sample) * e.gate_ld + n0;
-      float4* x = reinterpret_cast<float4*>(static_cast<float*>(e.out) + (long long)row * e.ldo + n0);
+    // x[row, n] += gate[sample, n] * (acc + bias[n]); the 32 rows of a round belong to one sample
+    const float g = __ldg(e.gate + (long long)(row0 / e.rows_per_sample) * e.gate_ld + n);
+    if (uniform_rows) {
+      float* px = static_cast<float*>(e.out) + (long long)orow0 * e.ldo + n;
+      float xin[32];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        float4 xv = x[i];
-        const float4 gv = __ldg(reinterpret_cast<const float4*>(g) + i);
-        const float4 bv = __ldg(reinterpret_cast<const float4*>(e.bias + n0) + i);
-        xv.x += gv.x * (v[4 * i] + bv.x);
-        xv.y += gv.y * (v[4 * i + 1] + bv.y);
-        xv.z += gv.z * (v[4 * i + 2] + bv.z);
-        xv.w += gv.w * (v[4 * i + 3] + bv.w);
-        x[i] = xv;
+      for (int j = 0; j < 32; ++j) xin[j] = px[(long long)j * e.ldo];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) px[(long long)j * e.ldo] = fmaf(g, val[j] + bias, xin[j]);
+    } else {
+#pragma unroll 4
+      for (int j = 0; j < 32; ++j) {
+        const int orow = __shfl_sync(0xffffffffu, orow_lane, j);
+        if (orow >= 0) {
+          float* px = static_cast<float*>(e.out) + (long long)orow * e.ldo + n;
+          *px = *px + g * (lds_f32(stage + 4u * (j * 32 + (lane ^ j))) + bias);
+        }
       }
     }
   } else if constexpr (EPI == EPI_QKV_ROPE) {
-    if (row_ok) {
-      const int D = e.heads * e.dh;
-      const int b = row / e.T, tok = row - b * e.T;
-      const int half_rot = e.rot_dim >> 1;
+    // q / k columns: + bias, rotary on interleaved pairs (partner column = lane ^ 1), head split
+    const int D = e.heads * e.dh;
+    const int which = n / D;
+    const int rem = n - which * D;
+    const int head = rem / e.dh;
+    const int d = rem - head * e.dh;
+    const bool rot = d < e.rot_dim;
+    const int half_rot = e.rot_dim >> 1;
+    const int b0 = row0 / e.T, tok0 = row0 - b0 * e.T;  // T is a multiple of 32: one sample per round
+    __half* qp = (which == 0 ? e.q : e.k) + (((long long)b0 * e.heads + head) * e.T + tok0) * e.dh_pad + d;
+    const float* cp = e.rope_cos + tok0 * half_rot + (d >> 1);
+    const float* sp = e.rope_sin + tok0 * half_rot + (d >> 1);
+    const float sgn = (d & 1) ? 1.f : -1.f;
+    const int nrows = p.M - row0 < 32 ? p.M - row0 : 32;
 #pragma unroll
-      for (int i = 0; i < 32; i += 2) {
-        const int n = n0 + i;
-        const int which = n / D;
-        const int rem = n - which * D;
-        const int head = rem / e.dh;
-        const int d = rem - head * e.dh;  // even
-        float x0 = v[i] + __ldg(e.bias + n);
-        float x1 = v[i + 1] + __ldg(e.bias + n + 1);
-        if (which < 2 && d < e.rot_dim) {
-          const float c = __ldg(e.rope_cos + tok * half_rot + (d >> 1));
-          const float s = __ldg(e.rope_sin + tok * half_rot + (d >> 1));
-          const float y0 = x0 * c - x1 * s;
-          const float y1 = x1 * c + x0 * s;
-          x0 = y0;
-          x1 = y1;
-        }
-        if (which == 2) {
-          // V is stored transposed, [B, heads, dh, T]: it is the K-major B operand of the P.V MMA (attention.cu).
-          // Consecutive lanes hold consecutive tokens, so each 2-byte store instruction covers 64 contiguous bytes.
-          __half* vt = e.v + (((long long)b * e.heads + head) * e.dh + d) * e.T + tok;
-          vt[0] = __float2half_rn(x0);
-          vt[e.T] = __float2half_rn(x1);
-        } else {
-          __half* base = which == 0 ? e.q : e.k;
-          __half2* dst =
-              reinterpret_cast<__half2*>(base + (((long long)b * e.heads + head) * e.T + tok) * e.dh_pad + d);
-          *dst = __floats2half2_rn(x0, x1);
-        }
-      }
+    for (int j = 0; j < 32; ++j) {
+      const float x = val[j] + bias;
+      const float px = __shfl_xor_sync(0xffffffffu, x, 1);
+      float y = x;
+      if (rot) y = fmaf(px * sgn, __ldg(sp + j * half_rot), x * __ldg(cp + j * half_rot));
+      if (j < nrows) qp[(long long)j * e.dh_pad] = __float2half_rn(y);
+    }
+  }
+  __syncwarp();  // the staging tile is rewritten by the next round
+}
+
+// row-per-thread epilogues: destination contiguous along rows (tokens / pixels)
+template <int EPI>
+__device__ __forceinline__ void epilogue_round_rows(const GemmParams& p, const uint32_t (&r)[32], int row, int n0) {
+  const EpiParams& e = p.epi;
+  if (row >= p.M) return;
+  if constexpr (EPI == EPI_QKV_ROPE) {
+    // V columns -> V^T [B, heads, dh, T]: it is the K-major B operand of the P.V MMA (attention.cu).  Consecutive
+    // lanes hold consecutive tokens, so each 2-byte store instruction covers 64 contiguous bytes.
+    const int D = e.heads * e.dh;
+    const int b = row / e.T, tok = row - b * e.T;
+    float bv[32];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float4 t = __ldg(reinterpret_cast<const float4*>(e.bias + n0) + i);
+      bv[4 * i] = t.x;
+      bv[4 * i + 1] = t.y;
+      bv[4 * i + 2] = t.z;
+      bv[4 * i + 3] = t.w;
+    }
+    const int rem0 = n0 - 2 * D;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      const int rem = rem0 + i;
+      const int head = rem / e.dh, d = rem - head * e.dh;
+      e.v[(((long long)b * e.heads + head) * e.dh + d) * e.T + tok] = __float2half_rn(__uint_as_float(r[i]) + bv[i]);
     }
   } else if constexpr (EPI == EPI_UNPATCH) {
-    if (row_ok) {
-      const int tokens = e.latH * e.tpt;
-      const int b = row / tokens, j = row - b * tokens;
-      const int time = j / e.tpt, part = j - time * e.tpt;
-      const int patch = e.latW / e.tpt;
-      float* out = static_cast<float*>(e.out);
+    const int tokens = e.latH * e.tpt;
+    const int b = row / tokens, j = row - b * tokens;
+    const int time = j / e.tpt, part = j - time * e.tpt;
+    const int patch = e.latW / e.tpt;
+    float* out = static_cast<float*>(e.out);
 #pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        const int f = n0 + i;
-        if (f < e.n_valid) {
-          const int pl = f / e.c_out, ch = f - pl * e.c_out;
-          const int pitch = part * patch + pl;
-          out[(((long long)b * e.c_out + ch) * e.latH + time) * e.latW + pitch] = v[i] + __ldg(e.bias + f);
-        }
+    for (int i = 0; i < 32; ++i) {
+      const int f = n0 + i;
+      if (f < e.n_valid) {
+        const int pl = f / e.c_out, ch = f - pl * e.c_out;
+        out[(((long long)b * e.c_out + ch) * e.latH + time) * e.latW + part * patch + pl] =
+            __uint_as_float(r[i]) + __ldg(e.bias + f);
       }
     }
   } else if constexpr (EPI == EPI_ROLL) {
-    if (row_ok) {
-      const int img = row >> 14, pix = row & 16383;  // 128 x 128 output pixels per VAE tile
-      const int h = pix >> 7, w = pix & 127;         // h = pitch, w = time within the tile
-      const int g = e.tile0 + img;                   // global tile index, tile-major: g = k * n_cand + cand
-      const int kt = g / e.n_cand, cand = g - kt * e.n_cand;
-      float* out = static_cast<float*>(e.out);
+    const int img = row >> 14, pix = row & 16383;  // 128 x 128 output pixels per VAE tile
+    const int h = pix >> 7, w = pix & 127;         // h = pitch, w = time within the tile
+    const int g = e.tile0 + img;                   // global tile index, tile-major: g = k * n_cand + cand
+    const int kt = g / e.n_cand, cand = g - kt * e.n_cand;
+    float* out = static_cast<float*>(e.out);
 #pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        const int ch = n0 + i;
-        if (ch < e.roll_ch)
-          out[(((long long)cand * e.roll_ch + ch) * 128 + h) * e.roll_len + kt * 128 + w] = v[i] + __ldg(e.bias + ch);
-      }
+    for (int i = 0; i < 32; ++i) {
+      const int ch = n0 + i;
+      if (ch < e.roll_ch)
+        out[(((long long)cand * e.roll_ch + ch) * 128 + h) * e.roll_len + kt * 128 + w] =
+            __uint_as_float(r[i]) + __ldg(e.bias + ch);
     }
   }
 }
 
 // ------------------------------------------------------------------------------------------------
-// the kernel: warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM owner), warps 2..5 = epilogue
-// persistent over tiles, double-buffered TMEM accumulator so the epilogue of tile i overlaps the
-// mainloop of tile i+1.
+// the kernel: warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM owner), warps 2..9 = epilogue.
+// Persistent over tiles, double-buffered TMEM accumulator so the epilogue of tile i overlaps the mainloop of
+// tile i+1.
 // ------------------------------------------------------------------------------------------------
-template <int BLOCK_N, int EPI>
+template <int BLOCK_N, int MT, int EPI>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                const __grid_constant__ GemmParams p) {
-  using Cfg = GemmCfg<BLOCK_N>;
+  using Cfg = GemmCfg<BLOCK_N, MT>;
   constexpr int STAGES = Cfg::STAGES;
+  constexpr uint32_t A_SUB = GEMM_BLOCK_M * GEMM_BLOCK_K * 2;
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + STAGES * Cfg::A_BYTES;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_b + STAGES * Cfg::B_BYTES);
+  float* smem_epi = reinterpret_cast<float*>(smem_b + STAGES * Cfg::B_BYTES);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(smem_epi) + Cfg::STAGE_BYTES_EPI);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full = empty_bar + STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
@@ -285,6 +346,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  // epilogue warps split one accumulator buffer (ACC_COLS TMEM columns) into two column halves of CW columns
+  constexpr int CW = (Cfg::ACC_COLS >= 64) ? Cfg::ACC_COLS / 2 : Cfg::ACC_COLS;
+  constexpr int EPI_ACTIVE = (Cfg::ACC_COLS >= 64) ? GEMM_EPI_WARPS : 4;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
@@ -295,7 +359,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], 4);
+      mbar_init(&tmem_empty[i], EPI_ACTIVE);
     }
     fence_barrier_init();
   }
@@ -308,7 +372,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int tiles_mn = p.num_m_tiles * p.num_n_tiles;
+  const int num_ms = (p.num_m_tiles + MT - 1) / MT;  // M super-tiles of MT x 128 rows
+  const int tiles_mn = num_ms * p.num_n_tiles;
   const int total_tiles = tiles_mn * p.num_par;
   const int num_kb = p.num_taps * p.kb_per_tap;
 
@@ -319,21 +384,29 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
         const int par = t / tiles_mn;
         const int tt = t - par * tiles_mn;
-        const int m_tile = tt / p.num_n_tiles;
-        const int n_tile = tt - m_tile * p.num_n_tiles;
-        const int img = m_tile / p.tiles_per_img;
-        const int rr = m_tile - img * p.tiles_per_img;
-        const int h0 = (rr / p.tiles_per_row) * p.bh;
-        const int w0 = (rr % p.tiles_per_row) * p.bw;
+        const int ms = tt / p.num_n_tiles;
+        const int n_tile = tt - ms * p.num_n_tiles;
         const int brow = par * p.N + n_tile * BLOCK_N;
-        const int bz = p.b_batched ? img : 0;
+        int img[MT], h0[MT], w0[MT];
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) {
+          const int m_tile = ms * MT + mt;  // may be == num_m_tiles for the odd tail: image index out of range -> zeros
+          img[mt] = m_tile / p.tiles_per_img;
+          const int rr = m_tile - img[mt] * p.tiles_per_img;
+          h0[mt] = (rr / p.tiles_per_row) * p.bh;
+          w0[mt] = (rr % p.tiles_per_row) * p.bw;
+        }
+        const int bz = p.b_batched ? img[0] : 0;
+        if (p.trace && blockIdx.x == 0) p.trace[(t / gridDim.x) * 8 + 0] = clock64();
         for (int tap = 0; tap < p.num_taps; ++tap) {
           const int dy = p.tap_dy[par][tap], dx = p.tap_dx[par][tap];
           for (int kc = 0; kc < p.kb_per_tap; ++kc) {
             mbar_wait(&empty_bar[stage], phase ^ 1);
             mbar_arrive_expect_tx(&full_bar[stage], Cfg::A_BYTES + Cfg::B_BYTES);
-            tma_load_4d(smem_a + stage * Cfg::A_BYTES, &tmap_a, &full_bar[stage], kc * GEMM_BLOCK_K, w0 + dx,
-                        h0 + dy, img);
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt)
+              tma_load_4d(smem_a + stage * Cfg::A_BYTES + mt * A_SUB, &tmap_a, &full_bar[stage], kc * GEMM_BLOCK_K,
+                          w0[mt] + dx, h0[mt] + dy, img[mt]);
             tma_load_3d(smem_b + stage * Cfg::B_BYTES, &tmap_b, &full_bar[stage],
                         (tap * p.kb_per_tap + kc) * GEMM_BLOCK_K, brow, bz);
             if (++stage == STAGES) {
@@ -352,16 +425,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+        if (p.trace && blockIdx.x == 0) p.trace[(t / gridDim.x) * 8 + 1] = clock64();
+        const uint32_t d_tmem = tmem_base + acc * Cfg::ACC_COLS;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          const uint64_t adesc = umma_desc_sw128(smem_a + stage * Cfg::A_BYTES);
+          if (kb == 0 && p.trace && blockIdx.x == 0) p.trace[(t / gridDim.x) * 8 + 2] = clock64();
           const uint64_t bdesc = umma_desc_sw128(smem_b + stage * Cfg::B_BYTES);
 #pragma unroll
-          for (int k = 0; k < GEMM_BLOCK_K / 16; ++k) {
-            // advance 16 fp16 = 32 bytes along K inside the 128-byte swizzle row: +2 in the (addr >> 4) field
-            umma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          for (int mt = 0; mt < MT; ++mt) {
+            const uint64_t adesc = umma_desc_sw128(smem_a + stage * Cfg::A_BYTES + mt * A_SUB);
+#pragma unroll
+            for (int k = 0; k < GEMM_BLOCK_K / 16; ++k) {
+              // advance 16 fp16 = 32 bytes along K inside the 128-byte swizzle row: +2 in the (addr >> 4) field
+              umma_f16(d_tmem + mt * BLOCK_N, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            }
           }
           umma_commit(&empty_bar[stage]);  // frees this smem stage when the MMAs above have read it
           if (++stage == STAGES) {
@@ -370,34 +448,78 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           }
         }
         umma_commit(&tmem_full[acc]);  // accumulator complete → epilogue
+        if (p.trace && blockIdx.x == 0) p.trace[(t / gridDim.x) * 8 + 3] = clock64();
         if (++acc == 2) {
           acc = 0;
           acc_phase ^= 1;
         }
       }
     }
-  } else {
-    const int quad = warp & 3;  // TMEM lane quadrant this warp may access
+  } else if (warp - 2 < EPI_ACTIVE) {
+    const int ew = warp - 2;
+    const int quad = warp & 3;   // TMEM lane quadrant this warp may access
+    const int chalf = ew >> 2;   // which half of the accumulator buffer's columns
+    const uint32_t stage_tile = smem_u32(smem_epi) + ew * 4096u;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
       const int par = t / tiles_mn;
       const int tt = t - par * tiles_mn;
-      const int m_tile = tt / p.num_n_tiles;
-      const int n_tile = tt - m_tile * p.num_n_tiles;
+      const int ms = tt / p.num_n_tiles;
+      const int n_tile = tt - ms * p.num_n_tiles;
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
-      const int row = m_tile * GEMM_BLOCK_M + quad * 32 + lane;
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BLOCK_N;
+      if (p.trace && blockIdx.x == 0 && warp == 2 && lane == 0) p.trace[(t / gridDim.x) * 8 + 4] = clock64();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * Cfg::ACC_COLS;
 #pragma unroll 1
-      for (int c = 0; c < BLOCK_N / 32; ++c) {
+      for (int c = 0; c < CW; c += 32) {
+        const int acc_col = chalf * CW + c;
+        const int mt = acc_col / BLOCK_N;
+        const int col = acc_col - mt * BLOCK_N;
+        const int m_tile = ms * MT + mt;
+        if (m_tile >= p.num_m_tiles) continue;  // odd tail of a 2-sub-tile tile
+        const int row0 = m_tile * GEMM_BLOCK_M + quad * 32;
+        const int n0 = n_tile * BLOCK_N + col;
         uint32_t r[32];
-        tmem_ld_32x32(taddr + c * 32, r);
+        const bool tracing = p.trace && blockIdx.x == 0 && warp == 2;
+        long long tq0 = 0;
+        if (tracing) tq0 = clock64();
+        tmem_ld_32x32(taddr + acc_col, r);
         tmem_ld_wait();
-        epilogue_chunk<EPI>(p, row, n_tile * BLOCK_N + c * 32, par, r);
+        if (tracing && lane == 0) p.trace[(t / gridDim.x) * 8 + 6] += clock64() - tq0;  // cycles inside tcgen05.ld
+        if constexpr (EPI == EPI_UNPATCH || EPI == EPI_ROLL) {
+          epilogue_round_rows<EPI>(p, r, row0 + lane, n0);
+        } else {
+          if constexpr (EPI == EPI_QKV_ROPE) {
+            if (n0 >= 2 * p.epi.heads * p.epi.dh) {  // V third of the QKV output (uniform per round)
+              epilogue_round_rows<EPI>(p, r, row0 + lane, n0);
+              continue;
+            }
+          }
+          // destination rows: lane i owns accumulator row row0 + i.  When all 32 rows are valid and equally spaced
+          // at the destination (always, except ragged tails and 16-pixel-wide upsample rows) the column loops use
+          // pointer increments; otherwise each row's destination is broadcast by shuffle.
+          const int row = row0 + lane;
+          int orow = row < p.M ? row : -1;
+          bool uniform_rows = row0 + 32 <= p.M;
+          int orow0 = row0, orow_step = 1;
+          if (p.epi.up2) {
+            const int hw = p.epi.upH * p.epi.upW;
+            if (orow >= 0) {
+              const int im = row / hw, rem = row - im * hw;
+              const int h = rem / p.epi.upW, w = rem - h * p.epi.upW;
+              orow = (im * (2 * p.epi.upH) + (2 * h + (par >> 1))) * (2 * p.epi.upW) + (2 * w + (par & 1));
+            }
+            uniform_rows = uniform_rows && (p.epi.upW % 32 == 0);
+            orow0 = __shfl_sync(0xffffffffu, orow, 0);
+            orow_step = 2;
+          }
+          epilogue_round_cols<EPI>(p, stage_tile, r, lane, row0, orow, uniform_rows, orow0, orow_step, n0, par);
+        }
       }
       tc_fence_before();
       __syncwarp();
+      if (p.trace && blockIdx.x == 0 && warp == 2 && lane == 0) p.trace[(t / gridDim.x) * 8 + 5] = clock64();
       if (lane == 0) mbar_arrive(&tmem_empty[acc]);
       if (++acc == 2) {
         acc = 0;

@@ -235,7 +235,7 @@ static int dit_forward_chunk(Dit* m, const float* x, const float* t, const long 
                              cudaStream_t st) {
   const int D = m->D, T = H * m->tpt;
   const long long M = (long long)B * T;
-  const long long Mp = round_up(M, 128), Bp = round_up(B, 128);
+  const long long Mp = round_up(M, 256), Bp = round_up(B, 256);
   Carver c(m->ws.ptr);
   __half* tok16 = c.take<__half>(Mp * m->K0);
   __half* h0_16 = c.take<__half>(Mp * 256);
@@ -369,7 +369,7 @@ static int dit_forward_chunk(Dit* m, const float* x, const float* t, const long 
 }
 
 static size_t dit_workspace_bytes(const Dit* m, int B, int T) {
-  const long long M = (long long)B * T, Mp = round_up(M, 128), Bp = round_up(B, 128);
+  const long long M = (long long)B * T, Mp = round_up(M, 256), Bp = round_up(B, 256);
   Carver c(nullptr);
   c.take<__half>(Mp * m->K0);
   c.take<__half>(Mp * 256);

@@ -114,6 +114,21 @@ cudaError_t launch_inst(const CUtensorMap& ma, const CUtensorMap& mb, const Gemm
   return cudaGetLastError();
 }
 
+template <int EPI>
+cudaError_t launch_sw(const CUtensorMap& mx, const CUtensorMap& mw, const GemmParams& p, int grid,
+                      cudaStream_t stream) {
+  static bool attr_set = false;
+  auto kern = gemm_sw_kernel<EPI>;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SW_SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  kern<<<grid, GEMM_THREADS, SW_SMEM_BYTES, stream>>>(mx, mw, p);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return cudaGetLastError();
+}
+
 }  // namespace
 
 unsigned long long gemm_launch_count() { return g_launches.load(); }
@@ -141,14 +156,20 @@ cudaError_t launch_gemm(const GemmDesc& d, cudaStream_t stream, std::string* err
 
   GemmParams p;
   std::memset(&p, 0, sizeof(p));
-  // a linear layer (H == 1) always uses 128-row boxes; rows past the end of A are zero-filled by TMA and masked
-  // in the epilogue.  Images use full-width boxes of bh rows.
-  const int bw = (d.H == 1 || d.W >= 128) ? 128 : d.W;
-  if (128 % bw != 0) return fail("gemm: W must divide 128 or be >= 128");
-  const int bh = 128 / bw;
+  const bool col_epi = d.epi == EPI_F16 || d.epi == EPI_F32 || d.epi == EPI_GATE_RESID || d.epi == EPI_QKV_ROPE;
+  // feature-major kernel (128 features x 256 rows per tile) for every feature count that is a multiple of 128;
+  // the row-major kernel with 32-column tiles serves the tiny outputs (final layer, conv_out) and odd widths
+  const bool sw = col_epi && d.N % SW_FEATS == 0 && d.block_n != 32;
+  const int rows_per_tile = sw ? SW_ROWS : GEMM_BLOCK_M;
+  // a linear layer (H == 1) uses boxes of rows_per_tile rows; rows past the end of A are zero-filled by TMA and
+  // masked in the epilogue.  Images use full-width boxes of bh rows.
+  const int bw = (d.H == 1 || d.W >= rows_per_tile) ? rows_per_tile : d.W;
+  if (rows_per_tile % bw != 0) return fail("gemm: image width must divide the row tile");
+  const int bh = rows_per_tile / bw;
   if (bh > 1 && d.H % bh != 0) return fail("gemm: H not a multiple of the tile height");
-  if (d.H > 1 && d.W > 128) return fail("gemm: images wider than 128 pixels are not supported");
-  if (d.n_img > 1 && d.H == 1 && d.W % 128 != 0) return fail("gemm: batched rows must be a multiple of 128");
+  if (d.H > 1 && d.W > rows_per_tile) return fail("gemm: images wider than the row tile are not supported");
+  if (d.n_img > 1 && d.H == 1 && d.W % rows_per_tile != 0)
+    return fail("gemm: batched rows must be a multiple of the row tile");
   p.bw = bw;
   p.bh = bh;
   p.tiles_per_row = (d.W + bw - 1) / bw;
@@ -156,6 +177,7 @@ cudaError_t launch_gemm(const GemmDesc& d, cudaStream_t stream, std::string* err
   p.M = d.n_img * d.H * d.W;
   p.N = d.N;
   p.num_m_tiles = d.n_img * p.tiles_per_img;
+  p.slots_per_par = (p.M + 31) / 32;
   p.kb_per_tap = d.C / GEMM_BLOCK_K;
   p.b_batched = d.b_batch > 1 ? 1 : 0;
   p.num_par = 1;
@@ -181,16 +203,17 @@ cudaError_t launch_gemm(const GemmDesc& d, cudaStream_t stream, std::string* err
   p.epi = d.e;
   p.trace = d.trace;
 
-  int bn = d.block_n;
-  if (bn == 0) {
-    const long long tiles128 = (long long)p.num_m_tiles * p.num_par * (d.N / 128 > 0 ? d.N / 128 : 1);
-    if (d.N % 256 == 0 && tiles128 / 2 >= 2LL * device_sm_count()) bn = 256;
-    else if (d.N % 128 == 0) bn = 128;
-    else bn = 32;
-  }
-  if (d.N % bn != 0) return fail("gemm: N must be a multiple of the N tile");
+  const int bn = sw ? SW_FEATS : 32;
+  if (d.N % bn != 0) return fail("gemm: N must be a multiple of 32");
+  if (!sw && d.epi != EPI_F16 && d.epi != EPI_F32 && d.epi != EPI_UNPATCH && d.epi != EPI_ROLL)
+    return fail("gemm: this epilogue needs N to be a multiple of 128");
   if (d.rows_b < p.num_par * d.N) return fail("gemm: B has fewer rows than num_par * N");
   p.num_n_tiles = d.N / bn;
+  if (d.epi == EPI_QKV_ROPE && (d.e.T % 32 != 0 || (d.e.heads * d.e.dh) % 32 != 0))
+    return fail("gemm: the QKV epilogue needs T and hidden to be multiples of 32");
+  if (d.epi == EPI_GATE_RESID && d.e.rows_per_sample % 32 != 0)
+    return fail("gemm: the gate/residual epilogue needs rows_per_sample to be a multiple of 32");
+  if ((long long)p.M * (d.conv == CONV_UP2 ? 4 : 1) >= (1LL << 31)) return fail("gemm: more than 2^31 output rows");
 
   CUtensorMap ma, mb;
   {
@@ -209,15 +232,7 @@ cudaError_t launch_gemm(const GemmDesc& d, cudaStream_t stream, std::string* err
     if (!make_map(&mb, d.B, 3, dims, strides, box, err)) return cudaErrorInvalidValue;
   }
 
-  // narrow outputs (N tile 128) process two 128-row sub-tiles per tile so the B stage is shared (see GemmCfg)
-  int mt = 1;
-  if (bn == 128 && (long long)(p.num_m_tiles / 2) * p.num_n_tiles * p.num_par >= device_sm_count()) mt = 2;
-  if (d.epi == EPI_QKV_ROPE && (d.e.T % 32 != 0 || (d.e.heads * d.e.dh) % 32 != 0))
-    return fail("gemm: the QKV epilogue needs T and hidden to be multiples of 32");
-  if (d.epi == EPI_GATE_RESID && d.e.rows_per_sample % 32 != 0)
-    return fail("gemm: the gate/residual epilogue needs rows_per_sample to be a multiple of 32");
-  if ((long long)p.M * (d.conv == CONV_UP2 ? 4 : 1) >= (1LL << 31)) return fail("gemm: more than 2^31 output rows");
-  const long long total = (long long)((p.num_m_tiles + mt - 1) / mt) * p.num_n_tiles * p.num_par;
+  const long long total = (long long)p.num_m_tiles * p.num_n_tiles * p.num_par;
   const int grid = (int)(total < device_sm_count() ? total : device_sm_count());
   if (grid <= 0) return cudaSuccess;
 
@@ -229,34 +244,26 @@ cudaError_t launch_gemm(const GemmDesc& d, cudaStream_t stream, std::string* err
   const double f_exec = 2.0 * rows * d.N * Kexec;
   const double f_alg = d.conv == CONV_UP2 ? 2.0 * rows * d.N * 9.0 * d.C : f_exec;
   if (g_prof_on.load(std::memory_order_relaxed))
-    snprintf(pname, sizeof pname, "gemm_tc conv%d K%d N%d epi%d bn%dx%d", d.conv, (int)Kexec, d.N, d.epi, bn, mt);
+    snprintf(pname, sizeof pname, "gemm_tc conv%d K%d N%d epi%d %s", d.conv, (int)Kexec, d.N, d.epi,
+             sw ? "f128xr256" : "r128xf32");
   ProfScope prof(pname, f_alg, f_exec, 0.0, stream);
 
   cudaError_t st = cudaErrorInvalidValue;
-#define RGM_CASE(BN, MT, EPI)                                          \
-  if (bn == BN && mt == MT && d.epi == EPI) {                          \
-    st = launch_inst<BN, MT, EPI>(ma, mb, p, grid, stream);            \
-    goto done;                                                         \
+  if (sw) {
+    switch (d.epi) {
+      case EPI_F16: st = launch_sw<EPI_F16>(ma, mb, p, grid, stream); break;
+      case EPI_F32: st = launch_sw<EPI_F32>(ma, mb, p, grid, stream); break;
+      case EPI_GATE_RESID: st = launch_sw<EPI_GATE_RESID>(ma, mb, p, grid, stream); break;
+      default: st = launch_sw<EPI_QKV_ROPE>(ma, mb, p, grid, stream); break;
+    }
+  } else {
+    switch (d.epi) {
+      case EPI_F16: st = launch_inst<32, 1, EPI_F16>(ma, mb, p, grid, stream); break;
+      case EPI_F32: st = launch_inst<32, 1, EPI_F32>(ma, mb, p, grid, stream); break;
+      case EPI_UNPATCH: st = launch_inst<32, 1, EPI_UNPATCH>(ma, mb, p, grid, stream); break;
+      default: st = launch_inst<32, 1, EPI_ROLL>(ma, mb, p, grid, stream); break;
+    }
   }
-  RGM_CASE(256, 1, EPI_F16)
-  RGM_CASE(128, 2, EPI_F16)
-  RGM_CASE(128, 1, EPI_F16)
-  RGM_CASE(32, 1, EPI_F16)
-  RGM_CASE(256, 1, EPI_F32)
-  RGM_CASE(128, 2, EPI_F32)
-  RGM_CASE(128, 1, EPI_F32)
-  RGM_CASE(32, 1, EPI_F32)
-  RGM_CASE(256, 1, EPI_GATE_RESID)
-  RGM_CASE(128, 2, EPI_GATE_RESID)
-  RGM_CASE(128, 1, EPI_GATE_RESID)
-  RGM_CASE(256, 1, EPI_QKV_ROPE)
-  RGM_CASE(128, 2, EPI_QKV_ROPE)
-  RGM_CASE(128, 1, EPI_QKV_ROPE)
-  RGM_CASE(32, 1, EPI_UNPATCH)
-  RGM_CASE(32, 1, EPI_ROLL)
-#undef RGM_CASE
-  return fail("gemm: no kernel instance for this (N tile, epilogue)");
-done:
   if (st != cudaSuccess && err) *err = std::string("gemm launch: ") + cudaGetErrorString(st);
   return st;
 }

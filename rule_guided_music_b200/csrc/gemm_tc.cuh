@@ -63,6 +63,7 @@ struct GemmParams {
   int num_taps, kb_per_tap;  // kb_per_tap = C / 64
   int tiles_per_img, tiles_per_row, bh, bw;
   int b_batched;              // B's third coordinate follows the image index (batched GEMM)
+  int slots_per_par;          // GroupNorm partial slots (32-row groups) per output parity = ceil(M / 32)
   signed char tap_dy[4][9];
   signed char tap_dx[4][9];
   // development aid: when non-null, CTA 0 writes clock64() at pipeline events of each of its tiles, 8 slots per tile:
@@ -115,13 +116,18 @@ __device__ __forceinline__ float apply_act(float x) {
 template <int ACT, bool RESID>
 __device__ __forceinline__ void cols_f16_fast(const float (&val)[32], __half* op, const __half* rp, long long ostride,
                                               long long rstride, float alpha, float bias, float& s, float& q) {
+  // The residual may alias the output (ResnetBlock shortcut written in place), so the compiler will not move a
+  // residual load above an earlier store: issue all 32 loads first, then the dependent stores (measured: a
+  // load -> store chain costs ~600 cycles per row).
+  __half rv[32];
+  if constexpr (RESID) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) rv[j] = rp[(long long)j * rstride];
+  }
 #pragma unroll
   for (int j = 0; j < 32; ++j) {
     float x = apply_act<ACT>(fmaf(val[j], alpha, bias));
-    if constexpr (RESID) {
-      x += __half2float(*rp);
-      rp += rstride;
-    }
+    if constexpr (RESID) x += __half2float(rv[j]);
     const __half h = __float2half_rn(x);
     *op = h;
     op += ostride;
@@ -131,22 +137,19 @@ __device__ __forceinline__ void cols_f16_fast(const float (&val)[32], __half* op
   }
 }
 
-template <int EPI>
-__device__ __forceinline__ void epilogue_round_cols(const GemmParams& p, uint32_t stage, const uint32_t (&r)[32],
-                                                    int lane, int row0, int orow_lane, bool uniform_rows,
-                                                    int orow0, int orow_step, int n0, int par) {
+// Column-owner epilogue core: thread `lane` owns output feature n and the 32 accumulator rows val[0..31] of the round
+// (rows row0..row0+31).  FROM_SMEM: the ragged/general path re-reads the values from the warp's staging tile
+// (row-major kernel) instead of indexing the register array dynamically.
+template <int EPI, bool FROM_SMEM>
+__device__ __forceinline__ void epilogue_cols_core(const GemmParams& p, const float (&val)[32], uint32_t stage,
+                                                   int lane, int row0, int orow_lane, bool uniform_rows, int orow0,
+                                                   int orow_step, int n, int par) {
   const EpiParams& e = p.epi;
-  // transpose: thread `lane` (a row) writes its 32 values; afterwards thread `lane` (a column) reads 32 rows.
-  // `stage` is the shared-space address of this warp's 32x32 fp32 tile; element (row, col) lives at
-  // row*32 + (col ^ row): conflict-free for both the row-wise writes and the column-wise reads.
-#pragma unroll
-  for (int c = 0; c < 32; ++c) sts_f32(stage + 4u * (lane * 32 + (c ^ lane)), __uint_as_float(r[c]));
-  __syncwarp();
-  float val[32];
-#pragma unroll
-  for (int j = 0; j < 32; ++j) val[j] = lds_f32(stage + 4u * (j * 32 + (lane ^ j)));
-  const int n = n0 + lane;
   const float bias = e.bias ? __ldg(e.bias + n) : 0.f;
+  auto value = [&](int j) -> float {
+    if constexpr (FROM_SMEM) return lds_f32(stage + 4u * (j * 32 + (lane ^ j)));
+    else return val[j];
+  };
 
   if constexpr (EPI == EPI_F16) {
     float s = 0.f, q = 0.f;
@@ -166,10 +169,10 @@ __device__ __forceinline__ void epilogue_round_cols(const GemmParams& p, uint32_
       }
     } else {
       // general path: ragged last rows, 16-pixel-wide upsample rows, gathered row-vector add
-#pragma unroll 4
+#pragma unroll
       for (int j = 0; j < 32; ++j) {
         const int orow = __shfl_sync(0xffffffffu, orow_lane, j);
-        float x = lds_f32(stage + 4u * (j * 32 + (lane ^ j))) * e.alpha + bias;
+        float x = value(j) * e.alpha + bias;
         if (orow >= 0) {
           if (e.addtab) x += __ldg(e.addtab + e.addidx[row0 + j] * (long long)p.N + n);
           if (e.act == ACT_SILU) x = silu_f(x);
@@ -190,7 +193,7 @@ __device__ __forceinline__ void epilogue_round_cols(const GemmParams& p, uint32_
       s += __shfl_xor_sync(0xffffffffu, s, 2);
       q += __shfl_xor_sync(0xffffffffu, q, 2);
       if ((lane & 3) == 0) {
-        const long long slot = (long long)par * (p.num_m_tiles * 4) + (row0 >> 5);
+        const long long slot = (long long)par * p.slots_per_par + (row0 >> 5);
         reinterpret_cast<float2*>(e.gn_part)[slot * (p.N >> 2) + (n >> 2)] = make_float2(s, q);
       }
     }
@@ -204,10 +207,10 @@ __device__ __forceinline__ void epilogue_round_cols(const GemmParams& p, uint32_
         op += ostride;
       }
     } else {
-#pragma unroll 4
+#pragma unroll
       for (int j = 0; j < 32; ++j) {
         const int orow = __shfl_sync(0xffffffffu, orow_lane, j);
-        float x = lds_f32(stage + 4u * (j * 32 + (lane ^ j))) * e.alpha + bias;
+        float x = value(j) * e.alpha + bias;
         if (orow >= 0) {
           if (e.addtab) x += __ldg(e.addtab + e.addidx[row0 + j] * (long long)p.N + n);
           if (e.act == ACT_SILU) x = silu_f(x);
@@ -227,12 +230,12 @@ __device__ __forceinline__ void epilogue_round_cols(const GemmParams& p, uint32_
 #pragma unroll
       for (int j = 0; j < 32; ++j) px[(long long)j * e.ldo] = fmaf(g, val[j] + bias, xin[j]);
     } else {
-#pragma unroll 4
+#pragma unroll
       for (int j = 0; j < 32; ++j) {
         const int orow = __shfl_sync(0xffffffffu, orow_lane, j);
         if (orow >= 0) {
           float* px = static_cast<float*>(e.out) + (long long)orow * e.ldo + n;
-          *px = *px + g * (lds_f32(stage + 4u * (j * 32 + (lane ^ j))) + bias);
+          *px = *px + g * (value(j) + bias);
         }
       }
     }
@@ -260,6 +263,22 @@ __device__ __forceinline__ void epilogue_round_cols(const GemmParams& p, uint32_
       if (j < nrows) qp[(long long)j * e.dh_pad] = __float2half_rn(y);
     }
   }
+}
+
+// Row-major kernel: tcgen05.ld hands thread i ROW i of the round; transpose the 32x32 block through the warp's
+// XOR-swizzled staging tile (element (row, col) at row*32 + (col ^ row): conflict-free both ways) so that thread i
+// owns column n0 + i, then run the column-owner core.
+template <int EPI>
+__device__ __forceinline__ void epilogue_round_cols(const GemmParams& p, uint32_t stage, const uint32_t (&r)[32],
+                                                    int lane, int row0, int orow_lane, bool uniform_rows,
+                                                    int orow0, int orow_step, int n0, int par) {
+#pragma unroll
+  for (int c = 0; c < 32; ++c) sts_f32(stage + 4u * (lane * 32 + (c ^ lane)), __uint_as_float(r[c]));
+  __syncwarp();
+  float val[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) val[j] = lds_f32(stage + 4u * (j * 32 + (lane ^ j)));
+  epilogue_cols_core<EPI, true>(p, val, stage, lane, row0, orow_lane, uniform_rows, orow0, orow_step, n0 + lane, par);
   __syncwarp();  // the staging tile is rewritten by the next round
 }
 
@@ -533,6 +552,223 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+// ================================================================================================================
+// Feature-major ("swapped") kernel: the workhorse for every output whose feature count is a multiple of 128.
+//
+// The UMMA computes D^T: M = 128 output FEATURES (A operand = the weight tile, 16 KB per k-block), N = 256 output
+// ROWS (B operand = the activation / im2col tile, 32 KB per k-block).  Compared with a 128-row x 128-feature tile this
+// halves the shared-memory operand reads per flop (96 B/clk instead of 128 B/clk -- a 128x128 UMMA is smem-bound) and
+// the L2 traffic per flop, for narrow layers (128-channel convolutions, N = 1152 / 3456 linears) as well as wide ones.
+// In TMEM a lane is a feature and a column is a row, which is exactly the "thread owns a feature, walks rows" layout
+// the coalesced epilogue wants: no shared-memory transposition, 64 / 128 contiguous bytes per store instruction.
+// ================================================================================================================
+constexpr int SW_ROWS = 256;      // output rows (pixels / tokens) per tile = UMMA N
+constexpr int SW_FEATS = 128;     // output features per tile = UMMA M
+constexpr int SW_STAGES = 4;
+constexpr uint32_t SW_W_BYTES = SW_FEATS * GEMM_BLOCK_K * 2;  // 16 KB
+constexpr uint32_t SW_X_BYTES = SW_ROWS * GEMM_BLOCK_K * 2;   // 32 KB
+constexpr size_t SW_SMEM_BYTES = 1024 + SW_STAGES * (SW_W_BYTES + SW_X_BYTES) + 256;
+
+template <int EPI>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_sw_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
+               const __grid_constant__ GemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_w = smem;
+  uint8_t* smem_x = smem + SW_STAGES * SW_W_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_x + SW_STAGES * SW_X_BYTES);
+  uint64_t* empty_bar = full_bar + SW_STAGES;
+  uint64_t* tmem_full = empty_bar + SW_STAGES;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_x);
+    tma_prefetch_desc(&tmap_w);
+    for (int i = 0; i < SW_STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], GEMM_EPI_WARPS);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // p.num_m_tiles counts 256-row tiles, p.num_n_tiles 128-feature tiles; feature tiles vary fastest so CTAs that run
+  // together share the activation tile in L2
+  const int tiles_mn = p.num_m_tiles * p.num_n_tiles;
+  const int total_tiles = tiles_mn * p.num_par;
+  const int num_kb = p.num_taps * p.kb_per_tap;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        const int par = t / tiles_mn;
+        const int tt = t - par * tiles_mn;
+        const int m_tile = tt / p.num_n_tiles;
+        const int n_tile = tt - m_tile * p.num_n_tiles;
+        const int img = m_tile / p.tiles_per_img;
+        const int rr = m_tile - img * p.tiles_per_img;
+        const int h0 = (rr / p.tiles_per_row) * p.bh;
+        const int w0 = (rr % p.tiles_per_row) * p.bw;
+        const int wrow = par * p.N + n_tile * SW_FEATS;
+        const int bz = p.b_batched ? img : 0;
+        if (p.trace && blockIdx.x == 0) p.trace[(t / gridDim.x) * 8 + 0] = clock64();
+        for (int tap = 0; tap < p.num_taps; ++tap) {
+          const int dy = p.tap_dy[par][tap], dx = p.tap_dx[par][tap];
+          for (int kc = 0; kc < p.kb_per_tap; ++kc) {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            mbar_arrive_expect_tx(&full_bar[stage], SW_W_BYTES + SW_X_BYTES);
+            tma_load_4d(smem_x + stage * SW_X_BYTES, &tmap_x, &full_bar[stage], kc * GEMM_BLOCK_K, w0 + dx, h0 + dy,
+                        img);
+            tma_load_3d(smem_w + stage * SW_W_BYTES, &tmap_w, &full_bar[stage],
+                        (tap * p.kb_per_tap + kc) * GEMM_BLOCK_K, wrow, bz);
+            if (++stage == SW_STAGES) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_f16(SW_FEATS, SW_ROWS);
+      int stage = 0, acc = 0;
+      uint32_t phase = 0, acc_phase = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        if (p.trace && blockIdx.x == 0) p.trace[(t / gridDim.x) * 8 + 1] = clock64();
+        const uint32_t d_tmem = tmem_base + acc * SW_ROWS;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          if (kb == 0 && p.trace && blockIdx.x == 0) p.trace[(t / gridDim.x) * 8 + 2] = clock64();
+          const uint64_t wdesc = umma_desc_sw128(smem_w + stage * SW_W_BYTES);
+          const uint64_t xdesc = umma_desc_sw128(smem_x + stage * SW_X_BYTES);
+#pragma unroll
+          for (int k = 0; k < GEMM_BLOCK_K / 16; ++k)
+            umma_f16(d_tmem, wdesc + 2 * k, xdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          umma_commit(&empty_bar[stage]);
+          if (++stage == SW_STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(&tmem_full[acc]);
+        if (p.trace && blockIdx.x == 0) p.trace[(t / gridDim.x) * 8 + 3] = clock64();
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
+      }
+    }
+  } else {
+    const int ew = warp - 2;
+    const int quad = warp & 3;   // TMEM lane quadrant = 32 features
+    const int rhalf = ew >> 2;   // which 128 of the tile's 256 rows
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      const int par = t / tiles_mn;
+      const int tt = t - par * tiles_mn;
+      const int m_tile = tt / p.num_n_tiles;
+      const int n_tile = tt - m_tile * p.num_n_tiles;
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      if (p.trace && blockIdx.x == 0 && warp == 2 && lane == 0) p.trace[(t / gridDim.x) * 8 + 4] = clock64();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * SW_ROWS + rhalf * 128;
+      const int n = n_tile * SW_FEATS + quad * 32 + lane;  // this thread's output feature
+#pragma unroll 1
+      for (int c = 0; c < 128; c += 32) {
+        const int row0 = m_tile * SW_ROWS + rhalf * 128 + c;
+        if (row0 >= p.M) break;
+        uint32_t r[32];
+        tmem_ld_32x32(taddr + c, r);
+        tmem_ld_wait();
+        if constexpr (EPI == EPI_QKV_ROPE) {
+          const int D = p.epi.heads * p.epi.dh;
+          if (n_tile * SW_FEATS + quad * 32 >= 2 * D) {
+            // V features -> V^T [B, heads, dh, T] (the K-major B operand of the P.V MMA): this thread holds 32
+            // consecutive tokens of one (head, d) row = 64 contiguous bytes
+            const EpiParams& e = p.epi;
+            const int rem = n - 2 * D;
+            const int head = rem / e.dh, d = rem - head * e.dh;
+            const int b0 = row0 / e.T, tok0 = row0 - b0 * e.T;
+            const float bias = __ldg(e.bias + n);
+            uint4 pk[4];
+            __half2* h2 = reinterpret_cast<__half2*>(pk);
+#pragma unroll
+            for (int j = 0; j < 32; j += 2)
+              h2[j >> 1] = __floats2half2_rn(__uint_as_float(r[j]) + bias, __uint_as_float(r[j + 1]) + bias);
+            __half* dst = e.v + (((long long)b0 * e.heads + head) * e.dh + d) * e.T + tok0;
+            if (row0 + 32 <= p.M) {
+#pragma unroll
+              for (int i = 0; i < 4; ++i) reinterpret_cast<uint4*>(dst)[i] = pk[i];
+            } else {
+              const __half* hv = reinterpret_cast<const __half*>(pk);
+              for (int j = 0; j < p.M - row0; ++j) dst[j] = hv[j];
+            }
+            continue;
+          }
+        }
+        float val[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) val[j] = __uint_as_float(r[j]);
+        // destination rows (see epilogue_cols_core)
+        const int row = row0 + lane;
+        int orow = row < p.M ? row : -1;
+        bool uniform_rows = row0 + 32 <= p.M;
+        int orow0 = row0, orow_step = 1;
+        if (p.epi.up2) {
+          const int hw = p.epi.upH * p.epi.upW;
+          if (orow >= 0) {
+            const int im = row / hw, rem = row - im * hw;
+            const int h = rem / p.epi.upW, w = rem - h * p.epi.upW;
+            orow = (im * (2 * p.epi.upH) + (2 * h + (par >> 1))) * (2 * p.epi.upW) + (2 * w + (par & 1));
+          }
+          uniform_rows = uniform_rows && (p.epi.upW % 32 == 0);
+          orow0 = __shfl_sync(0xffffffffu, orow, 0);
+          orow_step = 2;
+        }
+        epilogue_cols_core<EPI, false>(p, val, 0u, lane, row0, orow, uniform_rows, orow0, orow_step, n, par);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (p.trace && blockIdx.x == 0 && warp == 2 && lane == 0) p.trace[(t / gridDim.x) * 8 + 5] = clock64();
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
   }
 }
 

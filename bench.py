@@ -134,7 +134,7 @@ def run_reference(args):
 def run_b200(args):
     import torch.distributed as dist
 
-    from oracle import weights as ow  # seeded synthetic state dicts with the reference's keys (no checkpoints offline)
+    from rule_guided_music_b200 import synthetic_weights as ow  # seeded state dicts, reference keys (no checkpoints offline)
     from rule_guided_music_b200 import _lib
     from rule_guided_music_b200.guided_diffusion.condition_functions import model_fn
     from rule_guided_music_b200.guided_diffusion.dit import DiT_models

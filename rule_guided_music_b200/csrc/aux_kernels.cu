@@ -71,18 +71,16 @@ cudaError_t launch_timestep_embedding(const float* t, const float* freqs, __half
   return done();
 }
 
-__global__ void rope_table_kernel(const float* __restrict__ freqs, float* __restrict__ cosb, float* __restrict__ sinb,
-                                  int T, int nfreq) {
+__global__ void rope_table_kernel(const float* __restrict__ freqs, float2* __restrict__ cs, int T, int nfreq) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= T * nfreq) return;
   const int pos = i / nfreq, j = i - pos * nfreq;
   const float a = (float)pos * freqs[j];
-  cosb[i] = cosf(a);
-  sinb[i] = sinf(a);
+  cs[i] = make_float2(cosf(a), sinf(a));
 }
 
-cudaError_t launch_rope_table(const float* freqs, float* cosb, float* sinb, int T, int nfreq, cudaStream_t s) {
-  rope_table_kernel<<<(T * nfreq + 255) / 256, 256, 0, s>>>(freqs, cosb, sinb, T, nfreq);
+cudaError_t launch_rope_table(const float* freqs, float2* cs, int T, int nfreq, cudaStream_t s) {
+  rope_table_kernel<<<(T * nfreq + 255) / 256, 256, 0, s>>>(freqs, cs, T, nfreq);
   return done();
 }
 
@@ -333,41 +331,72 @@ cudaError_t launch_gn_finalize(const float* part, const float* gamma, const floa
   return done();
 }
 
+// grid = (pixel chunks, images).  A thread owns ONE 8-channel vector position (its GroupNorm coefficients stay in
+// registers) and walks the image's pixels with a stride, four 16-byte loads in flight; a warp covers 512 contiguous
+// bytes per load.  One fp16 read and one fp16 write per element.
+template <int SWISH>
 __global__ void __launch_bounds__(256) gn_apply_kernel(const __half* __restrict__ x, const float2* __restrict__ ab,
-                                                       __half* __restrict__ y, long long total_vec, int HW, int C,
-                                                       int swish) {
-  const int cv = C >> 3;  // 8-channel vectors per pixel
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total_vec;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int c8 = (int)(i % cv);
-    const long long pix = i / cv;
-    const long long img = pix / HW;
-    const uint4 u = __ldg(reinterpret_cast<const uint4*>(x) + i);
-    const float4* abp = reinterpret_cast<const float4*>(ab + img * C + c8 * 8);
+                                                       __half* __restrict__ y, int HW, int C) {
+  const int cv = C >> 3;                       // 8-channel vectors per pixel (16, 32 or 64)
+  const int c8 = threadIdx.x % cv;
+  const int prow = threadIdx.x / cv;           // pixel lane within the block
+  const int ppb = 256 / cv;                    // pixels per block iteration
+  const int img = blockIdx.y;
+  float a[8], b[8];
+  {
+    const float4* abp = reinterpret_cast<const float4*>(ab + (long long)img * C + c8 * 8);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float4 t = __ldg(abp + j);  // (a0, b0, a1, b1)
+      a[2 * j] = t.x;
+      b[2 * j] = t.y;
+      a[2 * j + 1] = t.z;
+      b[2 * j + 1] = t.w;
+    }
+  }
+  const uint4* xin = reinterpret_cast<const uint4*>(x) + (long long)img * HW * cv + c8;
+  uint4* yout = reinterpret_cast<uint4*>(y) + (long long)img * HW * cv + c8;
+  const int step = gridDim.x * ppb;
+  auto apply = [&](const uint4& u) -> uint4 {
     const __half2* h2 = reinterpret_cast<const __half2*>(&u);
     uint4 o;
     __half2* o2 = reinterpret_cast<__half2*>(&o);
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const float4 t = __ldg(abp + j);  // (a0, b0, a1, b1)
       const float2 f = __half22float2(h2[j]);
-      float v0 = t.x * f.x + t.y, v1 = t.z * f.y + t.w;
-      if (swish) {
+      float v0 = fmaf(a[2 * j], f.x, b[2 * j]), v1 = fmaf(a[2 * j + 1], f.y, b[2 * j + 1]);
+      if (SWISH) {
         v0 = __fdividef(v0, 1.0f + __expf(-v0));
         v1 = __fdividef(v1, 1.0f + __expf(-v1));
       }
       o2[j] = __floats2half2_rn(v0, v1);
     }
-    reinterpret_cast<uint4*>(y)[i] = o;
+    return o;
+  };
+  int p = blockIdx.x * ppb + prow;
+  for (; p + 3 * step < HW; p += 4 * step) {
+    uint4 u[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) u[i] = __ldcs(xin + (long long)(p + i * step) * cv);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) yout[(long long)(p + i * step) * cv] = apply(u[i]);
   }
+  for (; p < HW; p += step) yout[(long long)p * cv] = apply(__ldcs(xin + (long long)p * cv));
 }
 
 cudaError_t launch_gn_apply(const __half* x, const float2* ab, __half* y, int n, int HW, int C, int swish,
                             cudaStream_t s) {
-  if (C % 8 != 0) return cudaErrorInvalidValue;
+  if (C % 8 != 0 || 256 % (C / 8) != 0) return cudaErrorInvalidValue;
   const long long total_vec = (long long)n * HW * (C / 8);
   ProfScope prof("gn_apply", 0, 0, (double)total_vec * 32.0, s);
-  gn_apply_kernel<<<blocks_for(total_vec, 256 * 4, 148 * 16), 256, 0, s>>>(x, ab, y, total_vec, HW, C, swish);
+  const int ppb = 256 / (C / 8);
+  // enough blocks to fill the machine (~16 per SM) without making the per-thread loops shorter than one batch of 4
+  int chunks = (HW + ppb * 4 - 1) / (ppb * 4);
+  const int want = (148 * 16 + n - 1) / n;
+  if (chunks > want) chunks = want;
+  if (chunks < 1) chunks = 1;
+  if (swish) gn_apply_kernel<1><<<dim3(chunks, n), 256, 0, s>>>(x, ab, y, HW, C);
+  else gn_apply_kernel<0><<<dim3(chunks, n), 256, 0, s>>>(x, ab, y, HW, C);
   return done();
 }
 

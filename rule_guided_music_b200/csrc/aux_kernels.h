@@ -16,8 +16,8 @@ cudaError_t launch_patchify(const float* x, __half* tok, int B, int C, int H, in
 // TimestepEmbedder.timestep_embedding (dit.py:47-65): emb fp16 [B,2*half] = [cos(t f) | sin(t f)]
 cudaError_t launch_timestep_embedding(const float* t, const float* freqs, __half* emb, int B, int half, int ld,
                                       cudaStream_t s);
-// rotary tables (rotary_embedding_torch restated): cos/sin [T, nfreq] of pos * freq
-cudaError_t launch_rope_table(const float* freqs, float* cosb, float* sinb, int T, int nfreq, cudaStream_t s);
+// rotary tables (rotary_embedding_torch restated): (cos, sin) [T, nfreq] of pos * freq
+cudaError_t launch_rope_table(const float* freqs, float2* cs, int T, int nfreq, cudaStream_t s);
 // LayerNorm(no affine, eps) + modulate (dit.py:25-26, 321-335): out16[row] = LN(x[row])*(1+scale[b]) + shift[b],
 // b = row / rows_per_sample; shift/scale rows have stride mod_ld
 cudaError_t launch_ln_modulate(const float* x, const float* shift, const float* scale, int mod_ld, __half* out,

@@ -79,7 +79,7 @@ struct Dit {
   void* w16_arena = nullptr;
   void* f32_arena = nullptr;
   // rotary tables for the last T used
-  float *rope_cos = nullptr, *rope_sin = nullptr;
+  float2* rope_cs = nullptr;
   int rope_T = 0;
   bool rope_dirty = true;
   Workspace ws;
@@ -88,8 +88,7 @@ struct Dit {
   ~Dit() {
     if (w16_arena) cudaFree(w16_arena);
     if (f32_arena) cudaFree(f32_arena);
-    if (rope_cos) cudaFree(rope_cos);
-    if (rope_sin) cudaFree(rope_sin);
+    if (rope_cs) cudaFree(rope_cs);
   }
 };
 
@@ -307,8 +306,7 @@ static int dit_forward_chunk(Dit* m, const float* x, const float* t, const long 
       d.e.q = q16;
       d.e.k = k16;
       d.e.v = vt16;
-      d.e.rope_cos = m->rope_cos;
-      d.e.rope_sin = m->rope_sin;
+      d.e.rope_cs = m->rope_cs;
       d.e.T = T;
       d.e.heads = m->heads;
       d.e.dh = m->dh;
@@ -461,17 +459,15 @@ int rgm_dit_forward(rgm_dit* h, const float* x, const float* t, const long long*
     return set_error("rgm_dit_forward: " + std::to_string(T) + " tokens; this build supports 128 or 256 (latent H 64 or 128 at patch 8)");
   if (m->rope_dirty || m->rope_T < T) {
     if (m->rope_T < T) {
-      if (m->rope_cos) {
+      if (m->rope_cs) {
         cudaDeviceSynchronize();
-        cudaFree(m->rope_cos);
-        cudaFree(m->rope_sin);
+        cudaFree(m->rope_cs);
       }
       const int nf = m->rot / 2 > 0 ? m->rot / 2 : 1;
-      RGM_CUDA_OK(cudaMalloc(&m->rope_cos, (size_t)T * nf * sizeof(float)));
-      RGM_CUDA_OK(cudaMalloc(&m->rope_sin, (size_t)T * nf * sizeof(float)));
+      RGM_CUDA_OK(cudaMalloc(&m->rope_cs, (size_t)T * nf * sizeof(float2)));
       m->rope_T = T;
     }
-    if (m->rot > 0) RGM_CUDA_OK(launch_rope_table(m->rope_freqs, m->rope_cos, m->rope_sin, m->rope_T, m->rot / 2, st));
+    if (m->rot > 0) RGM_CUDA_OK(launch_rope_table(m->rope_freqs, m->rope_cs, m->rope_T, m->rot / 2, st));
     m->rope_dirty = false;
   }
   const int chunk = m->chunk < B ? m->chunk : B;

@@ -1,6 +1,7 @@
 // Host launcher for the tcgen05 implicit-GEMM kernel: builds the TMA tensor maps and picks the tile shape.
 #include <atomic>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <unordered_map>
@@ -202,6 +203,11 @@ cudaError_t launch_gemm(const GemmDesc& d, cudaStream_t stream, std::string* err
   }
   p.epi = d.e;
   p.trace = d.trace;
+  if (const char* tp = getenv("RGM_DEBUG_TRACE_PTR")) {  // development aid: trace every launch with a given epilogue
+    const char* te = getenv("RGM_DEBUG_TRACE_EPI");
+    if (te && atoi(te) == d.epi && (!getenv("RGM_DEBUG_TRACE_N") || atoi(getenv("RGM_DEBUG_TRACE_N")) == d.N))
+      p.trace = reinterpret_cast<unsigned long long*>(strtoull(tp, nullptr, 0));
+  }
 
   const int bn = sw ? SW_FEATS : 32;
   if (d.N % bn != 0) return fail("gemm: N must be a multiple of 32");

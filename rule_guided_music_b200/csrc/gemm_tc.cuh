@@ -43,8 +43,7 @@ struct EpiParams {
   __half* q;
   __half* k;
   __half* v;
-  const float* rope_cos;  // [T, rot_dim/2]
-  const float* rope_sin;
+  const float2* rope_cs;  // [T, rot_dim/2] (cos, sin) of position * frequency
   int T, heads, dh, dh_pad, rot_dim;
   // nearest-2x upsample output mapping (EPI_F16 with up2 = 1): low-res image dims
   int up2, upH, upW;
@@ -250,17 +249,25 @@ __device__ __forceinline__ void epilogue_cols_core(const GemmParams& p, const fl
     const int half_rot = e.rot_dim >> 1;
     const int b0 = row0 / e.T, tok0 = row0 - b0 * e.T;  // T is a multiple of 32: one sample per round
     __half* qp = (which == 0 ? e.q : e.k) + (((long long)b0 * e.heads + head) * e.T + tok0) * e.dh_pad + d;
-    const float* cp = e.rope_cos + tok0 * half_rot + (d >> 1);
-    const float* sp = e.rope_sin + tok0 * half_rot + (d >> 1);
+    // lanes outside the rotary dimensions read entry 0 and select (cos, sin) = (1, 0): uniform control flow, so the
+    // table loads of a whole half-round are issued back to back instead of one exposed load per row
+    const float2* tp = e.rope_cs + tok0 * half_rot + (rot ? (d >> 1) : 0);
     const float sgn = (d & 1) ? 1.f : -1.f;
     const int nrows = p.M - row0 < 32 ? p.M - row0 : 32;
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      const float x = val[j] + bias;
-      const float px = __shfl_xor_sync(0xffffffffu, x, 1);
-      float y = x;
-      if (rot) y = fmaf(px * sgn, __ldg(sp + j * half_rot), x * __ldg(cp + j * half_rot));
-      if (j < nrows) qp[(long long)j * e.dh_pad] = __float2half_rn(y);
+    for (int hh = 0; hh < 2; ++hh) {
+      float2 cs[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) cs[j] = __ldg(tp + (hh * 16 + j) * half_rot);
+#pragma unroll
+      for (int jj = 0; jj < 16; ++jj) {
+        const int j = hh * 16 + jj;
+        const float x = val[j] + bias;
+        const float px = __shfl_xor_sync(0xffffffffu, x, 1);
+        const float c = rot ? cs[jj].x : 1.f, sn = rot ? cs[jj].y : 0.f;
+        const float y = fmaf(px * sgn, sn, x * c);
+        if (j < nrows) qp[(long long)j * e.dh_pad] = __float2half_rn(y);
+      }
     }
   }
 }

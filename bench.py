@@ -132,35 +132,25 @@ def run_reference(args):
 # this repo
 # ----------------------------------------------------------------------------------------------------------------
 def run_b200(args):
-    import torch.distributed as dist
-
     from rule_guided_music_b200 import synthetic_weights as ow  # seeded state dicts, reference keys (no checkpoints offline)
     from rule_guided_music_b200 import _lib
+    from rule_guided_music_b200.guided_diffusion import dist_util
     from rule_guided_music_b200.guided_diffusion.condition_functions import model_fn
     from rule_guided_music_b200.guided_diffusion.dit import DiT_models
     from rule_guided_music_b200.guided_diffusion.script_util import create_diffusion
     from rule_guided_music_b200.taming.models.klvae_pedal import AutoencoderKL
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the B200 path has no CPU fallback (use --impl reference)")
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+    rank, world = dist_util.setup_dist(dev)
     B, N = args.batch, args.candidates
 
     # weights: rank 0 generates, NCCL broadcasts the packed fp32 state (dist_util.load_state_dict's job, dist_util.py:65-85)
-    sd = ow.make_dit_state_dict(seed=0)
-    vsd = ow.make_vae_state_dict(seed=1)
-    if world > 1:
-        for d_ in (sd, vsd):
-            for k in sorted(d_):
-                t = d_[k].to(dev)
-                dist.broadcast(t, src=0)
-                d_[k] = t
+    sd = dist_util.broadcast_state_dict(ow.make_dit_state_dict(seed=0 if rank == 0 else 7), dev, src=0)
+    vsd = dist_util.broadcast_state_dict(ow.make_vae_state_dict(seed=1 if rank == 0 else 8), dev, src=0)
     model = DiT_models["DiTRotary_XL_8"](input_size=[128, 16], in_channels=4, num_classes=3, learn_sigma=False)
     model.load_state_dict(sd, strict=False)
     model.to(dev).eval()
@@ -184,8 +174,7 @@ def run_b200(args):
                                          guidance_kwargs=GUIDANCE, scg_kwargs=scg, _t_host=int(T - 1 - (i % (T - 1))))["sample"]
 
     def barrier():
-        if world > 1:
-            dist.barrier()
+        dist_util.barrier()
         torch.cuda.synchronize()
 
     k = 0
@@ -234,18 +223,10 @@ def run_b200(args):
     prof = _lib.prof_summary()
     _lib.prof_enable(False)
 
-    def allmax(v):
-        if world == 1:
-            return v
-        t = torch.tensor([v], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return t.item()
-
-    ms, ms_e2e = allmax(ms), allmax(ms_e2e)
-    if world > 1:  # gather the finished latents once (scripts/cfg_sample.py:102-109), outside the timed region
-        gathered = [torch.empty_like(x) for _ in range(world)]
-        dist.all_gather(gathered, x)
-    finite = bool(torch.isfinite(x).all().item())
+    ms, ms_e2e = dist_util.max_over_ranks(ms, dev), dist_util.max_over_ranks(ms_e2e, dev)
+    # gather the finished latents once (scripts/cfg_sample.py:102-109), outside the timed region
+    gathered = dist_util.gather_samples(x)
+    finite = bool(torch.isfinite(gathered).all().item()) and gathered.shape[0] == world * B
     if rank == 0:
         peaks = {}
         try:
@@ -299,6 +280,8 @@ def run_b200(args):
                            ms / args.steps}, f, indent=1)
         print(json.dumps(line), flush=True)
     if world > 1:
+        import torch.distributed as dist
+
         dist.barrier()
         dist.destroy_process_group()
 

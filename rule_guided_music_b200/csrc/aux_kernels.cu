@@ -276,46 +276,50 @@ cudaError_t launch_gn_stats(const __half* x, const float* gamma, const float* be
   return done();
 }
 
-// Fold the conv epilogue's per-(32 rows x 4 channels) partial sums into per-(image, group) statistics in a fixed
-// order (deterministic), in double, and emit the per-channel affine.
-__global__ void __launch_bounds__(128) gn_finalize_kernel(const float* __restrict__ part,
+// Fold the conv epilogue's per-(128 rows x 4 channels) partial sums into per-(image, group) statistics in a fixed
+// order (deterministic), in double, and emit the per-channel affine.  One block per image: thread t owns quad
+// t % nq (consecutive threads read consecutive float2 -> coalesced) and every (256 / nq)-th slot.
+__global__ void __launch_bounds__(256) gn_finalize_kernel(const float* __restrict__ part,
                                                           const float* __restrict__ gamma,
                                                           const float* __restrict__ beta, float2* __restrict__ ab,
                                                           int slots_per_img, int n_par, long long par_stride, int C,
                                                           int HW_out, float eps) {
-  const int img = blockIdx.y, grp = blockIdx.x;
-  const int qpg = C / 128;  // 4-channel quads per group (1, 2 or 4)
-  const int nq = C / 4;
+  __shared__ double ss[256], qq[256];
+  __shared__ double gsum[32], gsq[32];
+  const int img = blockIdx.x;
+  const int nq = C / 4;          // 32, 64 or 128 quads
+  const int lanes = 256 / nq;    // slot lanes
+  const int qi = threadIdx.x % nq, sl0 = threadIdx.x / nq;
   const float2* p2 = reinterpret_cast<const float2*>(part);
   double s = 0.0, q = 0.0;
-  const int items = n_par * slots_per_img * qpg;
-  for (int i = threadIdx.x; i < items; i += blockDim.x) {
-    const int qi = i % qpg;
-    const int sl = (i / qpg) % slots_per_img;
-    const int par = i / (qpg * slots_per_img);
-    const long long slot = par * par_stride + (long long)img * slots_per_img + sl;
-    const float2 v = p2[slot * nq + grp * qpg + qi];
-    s += v.x;
-    q += v.y;
-  }
-  __shared__ double ss[128], qq[128];
+  for (int par = 0; par < n_par; ++par)
+    for (int sl = sl0; sl < slots_per_img; sl += lanes) {
+      const float2 v = p2[(par * par_stride + (long long)img * slots_per_img + sl) * nq + qi];
+      s += v.x;
+      q += v.y;
+    }
   ss[threadIdx.x] = s;
   qq[threadIdx.x] = q;
   __syncthreads();
-  for (int o = 64; o > 0; o >>= 1) {
-    if (threadIdx.x < o) {
-      ss[threadIdx.x] += ss[threadIdx.x + o];
-      qq[threadIdx.x] += qq[threadIdx.x + o];
-    }
-    __syncthreads();
+  const int qpg = C / 128;  // quads per group (1, 2 or 4)
+  if (threadIdx.x < 32) {
+    double a = 0.0, b = 0.0;
+    for (int l = 0; l < lanes; ++l)
+      for (int k = 0; k < qpg; ++k) {
+        a += ss[l * nq + threadIdx.x * qpg + k];
+        b += qq[l * nq + threadIdx.x * qpg + k];
+      }
+    gsum[threadIdx.x] = a;
+    gsq[threadIdx.x] = b;
   }
+  __syncthreads();
   const int cpg = C / 32;
-  if (threadIdx.x < cpg) {
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const int grp = c / cpg;
     const double n = (double)HW_out * cpg;
-    const double mean = ss[0] / n;
-    const double var = qq[0] / n - mean * mean;
+    const double mean = gsum[grp] / n;
+    const double var = gsq[grp] / n - mean * mean;
     const float rstd = (float)(1.0 / sqrt((var > 0 ? var : 0) + (double)eps));
-    const int c = grp * cpg + threadIdx.x;
     const float a = rstd * gamma[c];
     ab[(long long)img * C + c] = make_float2(a, beta[c] - (float)mean * a);
   }
@@ -324,10 +328,9 @@ __global__ void __launch_bounds__(128) gn_finalize_kernel(const float* __restric
 cudaError_t launch_gn_finalize(const float* part, const float* gamma, const float* beta, float2* ab, int n,
                                int slots_per_img, int n_par, long long par_stride, int C, int HW_out, float eps,
                                cudaStream_t s) {
-  if (C % 128 != 0) return cudaErrorInvalidValue;
+  if (C % 128 != 0 || C > 1024) return cudaErrorInvalidValue;
   ProfScope prof("gn_finalize", 0, 0, (double)n * n_par * slots_per_img * (C / 4) * 8.0, s);
-  gn_finalize_kernel<<<dim3(32, n), 128, 0, s>>>(part, gamma, beta, ab, slots_per_img, n_par, par_stride, C, HW_out,
-                                                 eps);
+  gn_finalize_kernel<<<n, 256, 0, s>>>(part, gamma, beta, ab, slots_per_img, n_par, par_stride, C, HW_out, eps);
   return done();
 }
 
@@ -397,6 +400,110 @@ cudaError_t launch_gn_apply(const __half* x, const float2* ab, __half* y, int n,
   if (chunks < 1) chunks = 1;
   if (swish) gn_apply_kernel<1><<<dim3(chunks, n), 256, 0, s>>>(x, ab, y, HW, C);
   else gn_apply_kernel<0><<<dim3(chunks, n), 256, 0, s>>>(x, ab, y, HW, C);
+  return done();
+}
+
+// norm_out (GroupNorm apply + swish, model.py:533-535) + conv_out 3x3 C -> out_ch (model.py:536) + assembly of the
+// piano roll (gaussian_diffusion.py:1355), on the CUDA cores: with 3 output channels the tensor-core tile would be
+// 90 % padding and the 9 shifted re-reads of the 128-channel input would dominate.  One block = 16x16 output pixels;
+// the 18x18 halo of the RAW input is loaded once, normalised + activated on the way into shared memory (zero for
+// out-of-image pixels: the conv pads the ACTIVATED tensor), then each thread accumulates its pixel's <= 4 outputs
+// in fp32 with fp32 weights.  Pixel stride in smem is padded by 16 B so the 16-byte loads of a warp's 32 consecutive
+// pixels hit distinct banks.
+__global__ void __launch_bounds__(256) vae_out_kernel(const __half* __restrict__ x, const float2* __restrict__ ab,
+                                                      const float* __restrict__ w, const float* __restrict__ bias,
+                                                      float* __restrict__ roll, int C, int out_ch, int tile0, int n_cand,
+                                                      int roll_len, int roll_ch) {
+  extern __shared__ uint8_t osm[];
+  const int pstride = C * 2 + 16;                       // bytes per halo pixel
+  uint8_t* halo = osm;                                  // [18*18][pstride]
+  float4* wsm = reinterpret_cast<float4*>(osm + ((18 * 18 * pstride + 15) & ~15));  // [9][C] (w0, w1, w2, w3)
+  float2* absm = reinterpret_cast<float2*>(wsm + 9 * C);                             // [C]
+  const int img = blockIdx.y;
+  const int by = blockIdx.x >> 3, bx = blockIdx.x & 7;  // 8 x 8 blocks of 16 x 16 pixels per 128 x 128 image
+  for (int i = threadIdx.x; i < C; i += 256) absm[i] = ab[(long long)img * C + i];
+  for (int i = threadIdx.x; i < 9 * C; i += 256) {
+    const int tap = i / C, c = i - tap * C;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    v.x = w[((long long)0 * C + c) * 9 + tap];
+    if (out_ch > 1) v.y = w[((long long)1 * C + c) * 9 + tap];
+    if (out_ch > 2) v.z = w[((long long)2 * C + c) * 9 + tap];
+    if (out_ch > 3) v.w = w[((long long)3 * C + c) * 9 + tap];
+    wsm[i] = v;
+  }
+  __syncthreads();
+  const int cv = C >> 3;
+  const __half* xin = x + (long long)img * 128 * 128 * C;
+  for (int i = threadIdx.x; i < 18 * 18 * cv; i += 256) {
+    const int pix = i / cv, c8 = i - pix * cv;
+    const int hy = pix / 18, hx = pix - hy * 18;
+    const int gy = by * 16 + hy - 1, gx = bx * 16 + hx - 1;
+    uint4 o = make_uint4(0u, 0u, 0u, 0u);
+    if (gy >= 0 && gy < 128 && gx >= 0 && gx < 128) {
+      const uint4 u = __ldg(reinterpret_cast<const uint4*>(xin + ((long long)gy * 128 + gx) * C) + c8);
+      const __half2* h2 = reinterpret_cast<const __half2*>(&u);
+      __half2* o2 = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = __half22float2(h2[j]);
+        const float2 a0 = absm[c8 * 8 + 2 * j], a1 = absm[c8 * 8 + 2 * j + 1];
+        float v0 = fmaf(a0.x, f.x, a0.y), v1 = fmaf(a1.x, f.y, a1.y);
+        v0 = __fdividef(v0, 1.0f + __expf(-v0));
+        v1 = __fdividef(v1, 1.0f + __expf(-v1));
+        o2[j] = __floats2half2_rn(v0, v1);  // the same fp16 rounding the stand-alone GroupNorm pass applies
+      }
+    }
+    *reinterpret_cast<uint4*>(halo + pix * pstride + c8 * 16) = o;
+  }
+  __syncthreads();
+  const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
+  float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
+#pragma unroll 1
+  for (int tap = 0; tap < 9; ++tap) {
+    const int dy = tap / 3, dx = tap - dy * 3;
+    const uint8_t* prow = halo + ((ty + dy) * 18 + tx + dx) * pstride;
+    const float4* wt = wsm + tap * C;
+#pragma unroll 4
+    for (int c8 = 0; c8 < cv; ++c8) {
+      const uint4 u = *reinterpret_cast<const uint4*>(prow + c8 * 16);
+      const __half2* h2 = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = __half22float2(h2[j]);
+        const float4 w0 = wt[c8 * 8 + 2 * j], w1 = wt[c8 * 8 + 2 * j + 1];
+        acc0 = fmaf(f.x, w0.x, acc0);
+        acc1 = fmaf(f.x, w0.y, acc1);
+        acc2 = fmaf(f.x, w0.z, acc2);
+        acc3 = fmaf(f.x, w0.w, acc3);
+        acc0 = fmaf(f.y, w1.x, acc0);
+        acc1 = fmaf(f.y, w1.y, acc1);
+        acc2 = fmaf(f.y, w1.z, acc2);
+        acc3 = fmaf(f.y, w1.w, acc3);
+      }
+    }
+  }
+  const int g = tile0 + img;  // global tile index, tile-major: g = k * n_cand + cand
+  const int kt = g / n_cand, cand = g - kt * n_cand;
+  const int h = by * 16 + ty, wcol = kt * 128 + bx * 16 + tx;
+  const float accs[4] = {acc0, acc1, acc2, acc3};
+#pragma unroll
+  for (int ch = 0; ch < 4; ++ch)
+    if (ch < roll_ch) roll[(((long long)cand * roll_ch + ch) * 128 + h) * roll_len + wcol] = accs[ch] + bias[ch];
+}
+
+cudaError_t launch_vae_out(const __half* x, const float2* ab, const float* w, const float* bias, float* roll, int n,
+                           int C, int out_ch, int tile0, int n_cand, int roll_len, int roll_ch, cudaStream_t s) {
+  if (C % 8 != 0 || out_ch < 1 || out_ch > 4 || roll_ch > out_ch) return cudaErrorInvalidValue;
+  const size_t smem = ((18 * 18 * (C * 2 + 16) + 15) & ~15) + (size_t)9 * C * sizeof(float4) + (size_t)C * sizeof(float2);
+  static size_t smem_set = 0;
+  if (smem > smem_set) {
+    cudaError_t e = cudaFuncSetAttribute(vae_out_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    smem_set = smem;
+  }
+  ProfScope prof("vae_out(norm+swish+conv_out+roll)", 2.0 * n * 16384.0 * out_ch * 9.0 * C, 2.0 * n * 16384.0 * 4 * 9.0 * C,
+                 (double)n * 16384.0 * (C * 2.0 + roll_ch * 4.0), s);
+  vae_out_kernel<<<dim3(64, n), 256, smem, s>>>(x, ab, w, bias, roll, C, out_ch, tile0, n_cand, roll_len, roll_ch);
   return done();
 }
 

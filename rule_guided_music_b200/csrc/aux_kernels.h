@@ -38,7 +38,7 @@ cudaError_t launch_vae_stem(const float* lat, float scale, const float* pq_w, co
 //   from the tensor itself (x fp16 NHWC [n, HW, C])
 cudaError_t launch_gn_stats(const __half* x, const float* gamma, const float* beta, float2* ab, int n, int HW, int C,
                             float eps, cudaStream_t s);
-//   from the partial sums a conv epilogue wrote (gemm_tc.cuh gn_part): slots_per_img 32-row slots per image and
+//   from the partial sums a conv epilogue wrote (gemm_tc.cuh gn_part): slots_per_img 128-row slots per image and
 //   parity, n_par parities (4 for the upsample conv), slot stride between parities = par_stride slots
 cudaError_t launch_gn_finalize(const float* part, const float* gamma, const float* beta, float2* ab, int n,
                                int slots_per_img, int n_par, long long par_stride, int C, int HW_out, float eps,
@@ -46,6 +46,10 @@ cudaError_t launch_gn_finalize(const float* part, const float* gamma, const floa
 // y = swish(a*x + b) (or a*x + b when swish == 0), fp16 NHWC
 cudaError_t launch_gn_apply(const __half* x, const float2* ab, __half* y, int n, int HW, int C, int swish,
                             cudaStream_t s);
+// norm_out + swish + conv_out (3x3, C -> out_ch <= 4, fp32 weights [out_ch,C,3,3]) + roll assembly, CUDA cores:
+// x fp16 NHWC [n,128,128,C] (raw, before GroupNorm), ab its GroupNorm affine, roll f32 [n_cand, roll_ch, 128, roll_len]
+cudaError_t launch_vae_out(const __half* x, const float2* ab, const float* w, const float* bias, float* roll, int n,
+                           int C, int out_ch, int tile0, int n_cand, int roll_len, int roll_ch, cudaStream_t s);
 // row softmax fp32 [rows, cols] -> fp16 (AttnBlock, model.py:183)
 cudaError_t launch_softmax_rows(const float* x, __half* y, long long rows, int cols, cudaStream_t s);
 // batched transpose fp16 [n, R, C] -> [n, C, R]

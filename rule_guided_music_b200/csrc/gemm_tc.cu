@@ -178,7 +178,7 @@ cudaError_t launch_gemm(const GemmDesc& d, cudaStream_t stream, std::string* err
   p.M = d.n_img * d.H * d.W;
   p.N = d.N;
   p.num_m_tiles = d.n_img * p.tiles_per_img;
-  p.slots_per_par = (p.M + 31) / 32;
+  p.slots_per_par = (p.M + 127) / 128;
   p.kb_per_tap = d.C / GEMM_BLOCK_K;
   p.b_batched = d.b_batch > 1 ? 1 : 0;
   p.num_par = 1;
@@ -214,6 +214,7 @@ cudaError_t launch_gemm(const GemmDesc& d, cudaStream_t stream, std::string* err
   if (!sw && d.epi != EPI_F16 && d.epi != EPI_F32 && d.epi != EPI_UNPATCH && d.epi != EPI_ROLL)
     return fail("gemm: this epilogue needs N to be a multiple of 128");
   if (d.rows_b < p.num_par * d.N) return fail("gemm: B has fewer rows than num_par * N");
+  if (!sw && d.e.gn_part != nullptr) return fail("gemm: GroupNorm partials need a feature count that is a multiple of 128");
   p.num_n_tiles = d.N / bn;
   if (d.epi == EPI_QKV_ROPE && (d.e.T % 32 != 0 || (d.e.heads * d.e.dh) % 32 != 0))
     return fail("gemm: the QKV epilogue needs T and hidden to be multiples of 32");

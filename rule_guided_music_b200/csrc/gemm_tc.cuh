@@ -51,8 +51,8 @@ struct EpiParams {
   int tpt, c_out, latH, latW, n_valid;
   // EPI_ROLL
   int tile0, n_cand, roll_len, roll_ch;
-  // optional GroupNorm partial statistics of the fp16 values just stored (EPI_F16):
-  // gn_part[par * num_m_tiles * 4 + row / 32][N / 4] = (sum, sumsq) over 32 rows x 4 channels
+  // optional GroupNorm partial statistics of the fp16 values just stored (EPI_F16, feature-major kernel):
+  // gn_part[par * ceil(M/128) + row / 128][N / 4] = (sum, sumsq) over 128 rows x 4 channels
   float* gn_part;
 };
 
@@ -62,7 +62,7 @@ struct GemmParams {
   int num_taps, kb_per_tap;  // kb_per_tap = C / 64
   int tiles_per_img, tiles_per_row, bh, bw;
   int b_batched;              // B's third coordinate follows the image index (batched GEMM)
-  int slots_per_par;          // GroupNorm partial slots (32-row groups) per output parity = ceil(M / 32)
+  int slots_per_par;          // GroupNorm partial slots (128-row groups) per output parity = ceil(M / 128)
   signed char tap_dy[4][9];
   signed char tap_dx[4][9];
   // development aid: when non-null, CTA 0 writes clock64() at pipeline events of each of its tiles, 8 slots per tile:
@@ -142,7 +142,7 @@ __device__ __forceinline__ void cols_f16_fast(const float (&val)[32], __half* op
 template <int EPI, bool FROM_SMEM>
 __device__ __forceinline__ void epilogue_cols_core(const GemmParams& p, const float (&val)[32], uint32_t stage,
                                                    int lane, int row0, int orow_lane, bool uniform_rows, int orow0,
-                                                   int orow_step, int n, int par) {
+                                                   int orow_step, int n, int par, float& s, float& q) {
   const EpiParams& e = p.epi;
   const float bias = e.bias ? __ldg(e.bias + n) : 0.f;
   auto value = [&](int j) -> float {
@@ -151,7 +151,7 @@ __device__ __forceinline__ void epilogue_cols_core(const GemmParams& p, const fl
   };
 
   if constexpr (EPI == EPI_F16) {
-    float s = 0.f, q = 0.f;
+    // s, q: running GroupNorm sums of this thread's feature over the rows it has stored (written by the caller)
     if (uniform_rows && e.addtab == nullptr) {
       __half* op = static_cast<__half*>(e.out) + (long long)orow0 * e.ldo + n;
       const long long ostride = (long long)orow_step * e.ldo;
@@ -183,17 +183,6 @@ __device__ __forceinline__ void epilogue_cols_core(const GemmParams& p, const fl
           s += f;
           q += f * f;
         }
-      }
-    }
-    if (e.gn_part != nullptr) {
-      // GroupNorm partials per (32 rows x 4 channels), no atomics (deterministic): lanes 4k..4k+3 hold one quad
-      s += __shfl_xor_sync(0xffffffffu, s, 1);
-      q += __shfl_xor_sync(0xffffffffu, q, 1);
-      s += __shfl_xor_sync(0xffffffffu, s, 2);
-      q += __shfl_xor_sync(0xffffffffu, q, 2);
-      if ((lane & 3) == 0) {
-        const long long slot = (long long)par * p.slots_per_par + (row0 >> 5);
-        reinterpret_cast<float2*>(e.gn_part)[slot * (p.N >> 2) + (n >> 2)] = make_float2(s, q);
       }
     }
   } else if constexpr (EPI == EPI_F32) {
@@ -285,7 +274,8 @@ __device__ __forceinline__ void epilogue_round_cols(const GemmParams& p, uint32_
   float val[32];
 #pragma unroll
   for (int j = 0; j < 32; ++j) val[j] = lds_f32(stage + 4u * (j * 32 + (lane ^ j)));
-  epilogue_cols_core<EPI, true>(p, val, stage, lane, row0, orow_lane, uniform_rows, orow0, orow_step, n0 + lane, par);
+  float s = 0.f, q = 0.f;  // (the row-major kernel does not emit GroupNorm partials)
+  epilogue_cols_core<EPI, true>(p, val, stage, lane, row0, orow_lane, uniform_rows, orow0, orow_step, n0 + lane, par, s, q);
   __syncwarp();  // the staging tile is rewritten by the next round
 }
 
@@ -706,6 +696,7 @@ gemm_sw_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
       if (p.trace && blockIdx.x == 0 && warp == 2 && lane == 0) p.trace[(t / gridDim.x) * 8 + 4] = clock64();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * SW_ROWS + rhalf * 128;
       const int n = n_tile * SW_FEATS + quad * 32 + lane;  // this thread's output feature
+      float gs = 0.f, gq = 0.f;  // GroupNorm sum / sum of squares of feature n over this warp's 128 rows
 #pragma unroll 1
       for (int c = 0; c < 128; c += 32) {
         const int row0 = m_tile * SW_ROWS + rhalf * 128 + c;
@@ -758,7 +749,22 @@ gemm_sw_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
           orow0 = __shfl_sync(0xffffffffu, orow, 0);
           orow_step = 2;
         }
-        epilogue_cols_core<EPI, false>(p, val, 0u, lane, row0, orow, uniform_rows, orow0, orow_step, n, par);
+        epilogue_cols_core<EPI, false>(p, val, 0u, lane, row0, orow, uniform_rows, orow0, orow_step, n, par, gs, gq);
+      }
+      if constexpr (EPI == EPI_F16) {
+        const int rbase = m_tile * SW_ROWS + rhalf * 128;
+        if (p.epi.gn_part != nullptr && rbase < p.M) {
+          // GroupNorm partials per (128 rows x 4 channels), no atomics (deterministic): lanes 4k..4k+3 hold one quad;
+          // gn_finalize_kernel folds quads into groups and sums an image's slots in a fixed order
+          gs += __shfl_xor_sync(0xffffffffu, gs, 1);
+          gq += __shfl_xor_sync(0xffffffffu, gq, 1);
+          gs += __shfl_xor_sync(0xffffffffu, gs, 2);
+          gq += __shfl_xor_sync(0xffffffffu, gq, 2);
+          if ((lane & 3) == 0) {
+            const long long slot = (long long)par * p.slots_per_par + (rbase >> 7);
+            reinterpret_cast<float2*>(p.epi.gn_part)[slot * (p.N >> 2) + (n >> 2)] = make_float2(gs, gq);
+          }
+        }
       }
       tc_fence_before();
       __syncwarp();

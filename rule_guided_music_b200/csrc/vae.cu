@@ -75,15 +75,31 @@ struct Vae {
   std::vector<std::vector<Res>> up;     // [level][block]
   std::vector<Conv> upsample;           // [level] (level 0 unused)
   Norm norm_out;
-  Conv conv_out;
+  float *cout_w = nullptr, *cout_b = nullptr;  // conv_out stays fp32: it runs fused on the CUDA cores (vae_out_kernel)
+  int cout_cin = 0;
   std::map<std::string, std::pair<float*, long long>> f32_keys;  // key -> (dst, numel)
   std::map<std::string, Conv*> conv_keys;                        // "<name>.weight" -> conv
   std::vector<void*> allocs;
-  DevBuf act[4], gnpart, abbuf, attn_s;
+  // Two independent chunk pipelines ("lanes"), each with its own activation buffers and stream: consecutive chunks
+  // alternate between them, so the HBM-bound GroupNorm passes of one chunk run while the tensor-bound convolutions
+  // of the other occupy the tcgen05 pipe (a GEMM CTA takes all shared memory of an SM but leaves registers and
+  // thread slots for an elementwise block).
+  struct Lane {
+    DevBuf act[4], gnpart, abbuf, attn_s;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t done = nullptr;
+  } lane[2];
+  cudaEvent_t fork = nullptr;
+  int n_lanes = 2;
   int chunk_tiles = 128;
 
   ~Vae() {
     for (void* p : allocs) cudaFree(p);
+    for (auto& l : lane) {
+      if (l.stream) cudaStreamDestroy(l.stream);
+      if (l.done) cudaEventDestroy(l.done);
+    }
+    if (fork) cudaEventDestroy(fork);
   }
   template <typename T>
   T* alloc(long long n) {
@@ -161,14 +177,19 @@ int vae_build(Vae* m) {
       ok = m->make_conv(m->upsample[lvl], "decoder.up." + std::to_string(lvl) + ".upsample.conv", block_in, block_in, 3,
                         CONV_UP2);
   }
-  ok = ok && m->make_norm(m->norm_out, "decoder.norm_out", block_in) &&
-       m->make_conv(m->conv_out, "decoder.conv_out", block_in, m->out_ch, 3, CONV_3x3);
-  if (!ok) return set_error("rgm_vae_create: out of memory");
+  ok = ok && m->make_norm(m->norm_out, "decoder.norm_out", block_in);
+  m->cout_cin = block_in;
+  m->cout_w = m->alloc<float>((long long)m->out_ch * block_in * 9);
+  m->cout_b = m->alloc<float>(m->out_ch);
+  if (!ok || !m->cout_w || !m->cout_b) return set_error("rgm_vae_create: out of memory");
+  m->f32_keys["decoder.conv_out.weight"] = {m->cout_w, (long long)m->out_ch * block_in * 9};
+  m->f32_keys["decoder.conv_out.bias"] = {m->cout_b, m->out_ch};
   return 0;
 }
 
 struct Ctx {
   Vae* m;
+  Vae::Lane* L;
   cudaStream_t st;
   int nt;  // tiles in this chunk
 };
@@ -199,7 +220,7 @@ int run_conv(Ctx& c, const Conv& cv, const __half* x, int H, const __half* resid
   d.e.alpha = 1.f;
   d.e.resid = resid;
   d.e.ldr = cv.cout;
-  d.e.gn_part = want_gn ? static_cast<float*>(c.m->gnpart.p) : nullptr;
+  d.e.gn_part = want_gn ? static_cast<float*>(c.L->gnpart.p) : nullptr;
   if (cv.kind == CONV_UP2) {
     d.e.up2 = 1;
     d.e.upH = H;
@@ -212,9 +233,9 @@ int run_conv(Ctx& c, const Conv& cv, const __half* x, int H, const __half* resid
 // GroupNorm affine (a, b) per (tile, channel) from the partials the last run_conv wrote
 int gn_from_part(Ctx& c, const Norm& n, int H_in, bool was_up2) {
   const int lowHW = H_in * H_in;
-  const long long par_stride = (long long)c.nt * lowHW / 32;
-  RGM_CUDA_OK(launch_gn_finalize(static_cast<float*>(c.m->gnpart.p), n.gamma, n.beta,
-                                 static_cast<float2*>(c.m->abbuf.p), c.nt, lowHW / 32, was_up2 ? 4 : 1, par_stride, n.c,
+  const long long par_stride = (long long)c.nt * lowHW / 128;
+  RGM_CUDA_OK(launch_gn_finalize(static_cast<float*>(c.L->gnpart.p), n.gamma, n.beta,
+                                 static_cast<float2*>(c.L->abbuf.p), c.nt, lowHW / 128, was_up2 ? 4 : 1, par_stride, n.c,
                                  was_up2 ? 4 * lowHW : lowHW, 1e-6f, c.st));
   return 0;
 }
@@ -224,10 +245,10 @@ int gn_from_part(Ctx& c, const Norm& n, int H_in, bool was_up2) {
 int run_res(Ctx& c, const Res& r, const __half* x, int H, bool x_from_up2, __half* t, __half* h, __half* out) {
   const int HW = H * H;
   if (gn_from_part(c, r.n1, x_from_up2 ? H / 2 : H, x_from_up2)) return -1;
-  RGM_CUDA_OK(launch_gn_apply(x, static_cast<float2*>(c.m->abbuf.p), t, c.nt, HW, r.n1.c, 1, c.st));
+  RGM_CUDA_OK(launch_gn_apply(x, static_cast<float2*>(c.L->abbuf.p), t, c.nt, HW, r.n1.c, 1, c.st));
   if (run_conv(c, r.c1, t, H, nullptr, h, true)) return -1;
   if (gn_from_part(c, r.n2, H, false)) return -1;
-  RGM_CUDA_OK(launch_gn_apply(h, static_cast<float2*>(c.m->abbuf.p), t, c.nt, HW, r.n2.c, 1, c.st));
+  RGM_CUDA_OK(launch_gn_apply(h, static_cast<float2*>(c.L->abbuf.p), t, c.nt, HW, r.n2.c, 1, c.st));
   const __half* resid = x;
   if (r.has_nin) {
     if (run_conv(c, r.nin, x, H, nullptr, out, false)) return -1;
@@ -236,12 +257,12 @@ int run_res(Ctx& c, const Res& r, const __half* x, int H, bool x_from_up2, __hal
   return run_conv(c, r.c2, t, H, resid, out, true);
 }
 
-int decode_chunk(Vae* m, const float* lat, float scale, float* roll, int n_cand, int Hlat, int roll_ch, int tile0,
-                 int nt, cudaStream_t st) {
-  Ctx c{m, st, nt};
+int decode_chunk(Vae* m, Vae::Lane* L, const float* lat, float scale, float* roll, int n_cand, int Hlat, int roll_ch,
+                 int tile0, int nt, cudaStream_t st) {
+  Ctx c{m, L, st, nt};
   __half* buf[4];
-  for (int i = 0; i < 4; ++i) buf[i] = static_cast<__half*>(m->act[i].p);
-  float2* ab = static_cast<float2*>(m->abbuf.p);
+  for (int i = 0; i < 4; ++i) buf[i] = static_cast<__half*>(L->act[i].p);
+  float2* ab = static_cast<float2*>(L->abbuf.p);
   int H = 16;
   int C = m->block_in0;
   // stem
@@ -277,7 +298,7 @@ int decode_chunk(Vae* m, const float* lat, float scale, float* roll, int n_cand,
     if (run_conv(c, m->attn_k, hn, H, nullptr, k, false)) return -1;
     if (run_conv(c, m->attn_v, hn, H, nullptr, v, false)) return -1;
     RGM_CUDA_OK(launch_transpose(v, vT, nt, HW, C, st));
-    float* S = static_cast<float*>(m->attn_s.p);
+    float* S = static_cast<float*>(L->attn_s.p);
     {
       GemmDesc d;  // S[b] = q[b] k[b]^T * C^-0.5
       d.A = q;
@@ -342,33 +363,12 @@ int decode_chunk(Vae* m, const float* lat, float scale, float* roll, int n_cand,
       from_up = true;
     }
   }
-  // norm_out + swish + conv_out, scattered into the roll
+  // norm_out + swish + conv_out, assembled into the roll: one fused CUDA-core kernel (aux_kernels.cu)
   {
-    const int HW = H * H;
     if (gn_from_part(c, m->norm_out, from_up ? H / 2 : H, from_up)) return -1;
-    __half* t = buf[(cur + 1) & 3];
-    RGM_CUDA_OK(launch_gn_apply(buf[cur], ab, t, nt, HW, m->norm_out.c, 1, st));
-    if (H != 128) return set_error("rgm_vae: decoder output is not 128x128 (EPI_ROLL assumes 128x128 tiles)");
-    GemmDesc d;
-    d.A = t;
-    d.n_img = nt;
-    d.H = H;
-    d.W = H;
-    d.C = m->conv_out.cin;
-    d.lda = m->conv_out.cin;
-    d.B = m->conv_out.w;
-    d.N = m->conv_out.cout_pad;
-    d.rows_b = m->conv_out.cout_pad;
-    d.conv = CONV_3x3;
-    d.epi = EPI_ROLL;
-    d.block_n = 32;
-    d.e.out = roll;
-    d.e.bias = m->conv_out.b;
-    d.e.tile0 = tile0;
-    d.e.n_cand = n_cand;
-    d.e.roll_len = 8 * Hlat;
-    d.e.roll_ch = roll_ch;
-    RGM_VGEMM_OK(d);
+    if (H != 128) return set_error("rgm_vae: decoder output is not 128x128 (the roll kernels assume 128x128 tiles)");
+    RGM_CUDA_OK(launch_vae_out(buf[cur], ab, m->cout_w, m->cout_b, roll, nt, m->norm_out.c, m->out_ch, tile0, n_cand,
+                               8 * Hlat, roll_ch, st));
   }
   return 0;
 }
@@ -385,7 +385,7 @@ int rgm_vae_create(rgm_vae** out, int ch, const int* ch_mult, int n_levels, int 
   if (rgm_check_device()) return -1;
   if (!out || !ch_mult || n_levels < 1 || n_levels > 8) return set_error("rgm_vae_create: bad arguments");
   if (z_channels != 4) return set_error("rgm_vae_create: the fused stem is written for z_channels = 4");
-  if (out_ch > 32) return set_error("rgm_vae_create: out_ch > 32");
+  if (out_ch > 4) return set_error("rgm_vae_create: out_ch > 4 (the fused conv_out kernel keeps <= 4 accumulators)");
   Vae* m = new Vae();
   m->ch = ch;
   m->n_levels = n_levels;
@@ -403,6 +403,7 @@ int rgm_vae_create(rgm_vae** out, int ch, const int* ch_mult, int n_levels, int 
     return set_error("rgm_vae_create: this build decodes 16x16 latent tiles to 128x128 (4 levels)");
   }
   if (const char* e = getenv("RGM_VAE_CHUNK")) m->chunk_tiles = atoi(e) > 0 ? atoi(e) : m->chunk_tiles;
+  if (const char* e = getenv("RGM_VAE_LANES")) m->n_lanes = atoi(e) >= 2 ? 2 : 1;
   if (vae_build(m) != 0) {
     delete m;
     return -1;
@@ -458,13 +459,40 @@ int rgm_vae_decode_latents(rgm_vae* h, const float* lat, float scale_factor, flo
     maxc = std::max(maxc, hw * std::max(cmax, (long long)m->ch * m->mult[l]));
   }
   maxc = std::max(maxc, 4LL * 256 * m->block_in0);  // the attention block carves 3-4 tensors out of one buffer
-  for (int i = 0; i < 4; ++i) RGM_CUDA_OK(m->act[i].reserve((size_t)chunk * maxc * sizeof(__half)));
-  RGM_CUDA_OK(m->gnpart.reserve((size_t)chunk * maxc / 8 + 1024));
-  RGM_CUDA_OK(m->abbuf.reserve((size_t)chunk * 512 * sizeof(float2) * 2));
-  RGM_CUDA_OK(m->attn_s.reserve((size_t)chunk * 256 * 256 * sizeof(float)));
-  for (int t0 = 0; t0 < total; t0 += chunk) {
+  const int n_chunks = (total + chunk - 1) / chunk;
+  const int lanes = (m->n_lanes > 1 && n_chunks > 1) ? 2 : 1;
+  for (int l = 0; l < lanes; ++l) {
+    Vae::Lane& L = m->lane[l];
+    for (int i = 0; i < 4; ++i) RGM_CUDA_OK(L.act[i].reserve((size_t)chunk * maxc * sizeof(__half)));
+    RGM_CUDA_OK(L.gnpart.reserve((size_t)chunk * maxc / 8 + 1024));
+    RGM_CUDA_OK(L.abbuf.reserve((size_t)chunk * 512 * sizeof(float2) * 2));
+    RGM_CUDA_OK(L.attn_s.reserve((size_t)chunk * 256 * 256 * sizeof(float)));
+  }
+  if (lanes == 1) {
+    for (int t0 = 0; t0 < total; t0 += chunk) {
+      const int nt = (total - t0) < chunk ? (total - t0) : chunk;
+      if (decode_chunk(m, &m->lane[0], lat, scale_factor, roll, n_cand, Hlat, roll_ch, t0, nt, st) != 0) return -1;
+    }
+    return 0;
+  }
+  // fork: both lane streams start after everything already enqueued on the caller's stream ...
+  if (!m->fork) RGM_CUDA_OK(cudaEventCreateWithFlags(&m->fork, cudaEventDisableTiming));
+  for (int l = 0; l < 2; ++l) {
+    if (!m->lane[l].stream) RGM_CUDA_OK(cudaStreamCreateWithFlags(&m->lane[l].stream, cudaStreamNonBlocking));
+    if (!m->lane[l].done) RGM_CUDA_OK(cudaEventCreateWithFlags(&m->lane[l].done, cudaEventDisableTiming));
+  }
+  RGM_CUDA_OK(cudaEventRecord(m->fork, st));
+  for (int l = 0; l < 2; ++l) RGM_CUDA_OK(cudaStreamWaitEvent(m->lane[l].stream, m->fork, 0));
+  int ci = 0;
+  for (int t0 = 0; t0 < total; t0 += chunk, ++ci) {
     const int nt = (total - t0) < chunk ? (total - t0) : chunk;
-    if (decode_chunk(m, lat, scale_factor, roll, n_cand, Hlat, roll_ch, t0, nt, st) != 0) return -1;
+    Vae::Lane& L = m->lane[ci & 1];
+    if (decode_chunk(m, &L, lat, scale_factor, roll, n_cand, Hlat, roll_ch, t0, nt, L.stream) != 0) return -1;
+  }
+  // ... and join: the caller's stream continues after both lanes
+  for (int l = 0; l < 2; ++l) {
+    RGM_CUDA_OK(cudaEventRecord(m->lane[l].done, m->lane[l].stream));
+    RGM_CUDA_OK(cudaStreamWaitEvent(st, m->lane[l].done, 0));
   }
   return 0;
 }

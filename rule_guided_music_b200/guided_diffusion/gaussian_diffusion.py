@@ -153,6 +153,8 @@ class GaussianDiffusion:
         self._dev_tables = {}
         # record=True bookkeeping (reference :778-787)
         self.log_probs, self.each_loss = [], {}
+        # debugging / test hook: when set to a list, every SCG decision appends (total_log_prob [N, B], chosen index [B])
+        self._trace = None
 
     # ---- device-resident tables ----------------------------------------------------------------------------------
     def _tables(self, device):
@@ -362,6 +364,8 @@ class GaussianDiffusion:
             sample = th.empty_like(mean_c)
             _lib.call("rgm_scg_select", _lib.ptr(total), _lib.ptr(cand), _lib.ptr(sample), _lib.ptr(idx), N, B, elems,
                       stream)
+            if self._trace is not None:
+                self._trace.append((total.view(N, B).clone(), idx.clone()))
             if record:
                 self._record(t, total, idx, each, N, B)
             return sample
@@ -388,6 +392,8 @@ class GaussianDiffusion:
             seg_out = th.empty(B, *seg_cand.shape[2:], device=dev, dtype=th.float32)
             _lib.call("rgm_scg_select", _lib.ptr(total), _lib.ptr(seg_cand), _lib.ptr(seg_out), _lib.ptr(idx), N, B,
                       seg_out[0].numel(), stream)
+            if self._trace is not None:
+                self._trace.append((total.view(N, B).clone(), idx.clone()))
             subs.append(seg_out)
         return th.concat(subs, dim=-2)
 

@@ -171,7 +171,87 @@ def golden_sampler():
     save("sampler", **out)
 
 
+def golden_sampler_ext():
+    """Classifier-guidance hook, replacement editing, DiffCollage workers, per-segment selection, final uint8 decode --
+    all through the reference's own code."""
+    import diff_collage as dc  # the reference's package
+    from guided_diffusion.condition_functions import dc_model_fn
+    from guided_diffusion.midi_util import decode_sample_for_midi
+
+    embed = build_ref_vae()
+    out = {}
+    # spy on the losses so the goldens also carry, per step, the smallest relative margin between the best and the
+    # runner-up candidate: a test may only insist on the same choice where the reference's own decision is not a
+    # near-tie (random-weight models give nearly identical candidates)
+    calls = []
+    real_losses = dict(gd.LOSS_DICT)
+
+    def spy(name):
+        def f(gen, y):
+            loss = real_losses[name](gen, y)
+            calls.append((name, loss.clone()))
+            return loss
+        return f
+
+    for name in list(gd.LOSS_DICT):
+        gd.LOSS_DICT[name] = spy(name)
+
+    def step_totals(cfg):
+        """total_log_prob [N, B] of every argmax decision made since the last call (gaussian_diffusion.py:531-540)."""
+        rules = cfg["rules"]
+        n = cfg["scg"]["num_samples"]
+        totals = []
+        for i in range(0, len(calls), len(rules)):
+            total = 0
+            for name, loss in calls[i:i + len(rules)]:
+                total = total + (-loss) * cfg["scg"].get(name, 1.0)
+            totals.append(total.view(n, -1).numpy().copy())
+        calls.clear()
+        return totals
+
+    for tag, cfg in gi.EXT_CASES.items():
+        model, _ = build_ref_dit(gi.DIT_CASES[cfg["dit"]])
+        diffusion = create_diffusion(timestep_respacing=cfg["respacing"])
+        if cfg.get("dc"):
+            def eps_fn(x, t, y=None, model=model):
+                return model(x.permute(0, 1, 3, 2), t, y=y).permute(0, 1, 3, 2)
+            if cfg["dc"]["type"] == "circle":
+                worker = dc.CondIndCircle((4, 16, 128), eps_fn, cfg["dc"]["num_img"] + 1, overlap_size=64)
+            else:
+                worker = dc.CondIndSimple((4, 16, 128), eps_fn, cfg["dc"]["num_img"], overlap_size=64)
+            assert (cfg["shape"][2], cfg["shape"][3]) == (worker.shape[2], worker.shape[1])
+            fn = partial(dc_model_fn, model=worker.eps_scalar_t_fn, num_classes=3, class_cond=True, cfg=False, w=0.0)
+        else:
+            fn = partial(model_fn, model=model, num_classes=3, class_cond=True, cfg=False, w=0.0)
+        g = dict(cfg["guidance"])
+        if "dc" in g:
+            g["dc"] = SimpleNamespace(**g["dc"])
+        guidance = SimpleNamespace(**g)
+        loop = diffusion.ddim_sample_loop_progressive if cfg["ddim"] else diffusion.p_sample_loop_progressive
+        extra = {"eta": cfg["eta"]} if cfg["ddim"] else {}
+        diffusion.t_end = 0
+        torch.manual_seed(cfg["seed"])
+        steps, totals, ndec = [], [], []
+        calls.clear()
+        for o in loop(fn, cfg["shape"], model_kwargs=gi.ext_model_kwargs(cfg), device="cpu", embed_model=embed,
+                      scale_factor=gi.SCALE_FACTOR, guidance_kwargs=guidance, scg_kwargs=dict(cfg["scg"]),
+                      cond_fn=gi.analytic_cond_fn if cfg.get("cond") else None,
+                      edit_kwargs=gi.edit_inputs() if cfg.get("edit") else None, **extra):
+            steps.append(o["sample"].numpy().copy())
+            tt = step_totals(cfg)
+            totals += tt
+            ndec.append(len(tt))
+        out[tag] = np.stack(steps)
+        out[tag + "__totals"] = np.stack(totals)      # [decisions, N, B], in call order
+        out[tag + "__ndec"] = np.array(ndec)           # decisions per step
+        del model
+    for name, fn_ in real_losses.items():
+        gd.LOSS_DICT[name] = fn_
+    out["midi_roll"] = decode_sample_for_midi(gi.vae_latents(), embed, gi.SCALE_FACTOR, threshold=-0.95).numpy()
+    save("sampler_ext", **out)
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["schedule", "rules", "dit", "vae", "sampler"]
+    which = sys.argv[1:] or ["schedule", "rules", "dit", "vae", "sampler", "sampler_ext"]
     for w in which:
         globals()["golden_" + w]()

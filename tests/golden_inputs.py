@@ -141,3 +141,48 @@ def sampler_model_kwargs(cfg):
     if cfg.get("rules"):
         kw["rule"] = rule_targets(B, H * 8, cfg["rules"])
     return kw
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# extended sampler cases: classifier-guidance hook, replacement editing, DiffCollage long sequences (+ per-segment
+# selection), final decode to the uint8 roll.  Goldens in tests/golden/sampler_ext.npz
+# ---------------------------------------------------------------------------------------------------------------
+def analytic_cond_fn(x, t, y=None, rule=None):
+    """Stand-in for a classifier-gradient hook (condition_functions.py:58-85): deterministic, no autograd."""
+    return -(x - 0.3) * 0.5
+
+
+def edit_inputs(device="cpu"):
+    g = torch.Generator(device="cpu").manual_seed(31)
+    gt = torch.randn(1, 4, 128, 16, generator=g) * 0.7
+    mask = torch.zeros(1, 1, 128, 1)
+    mask[:, :, :64] = 1.0
+    return {"gt": gt.to(device), "mask": mask.to(device), "noise_level": 3, "l_start": 64, "l_end": 128}
+
+
+EXT_CASES = {
+    # DDPM + SCG + classifier guidance applied at every step (gaussian_diffusion.py:691)
+    "ddpm_scg_cond": dict(dit="small", respacing="4", ddim=False, shape=(2, 4, 64, 16), seed=7,
+                          scg=dict(num_samples=2, pitch_hist=1.0), guidance=_GUIDE_ON, rules=["pitch_hist"],
+                          cond=True),
+    # replacement-based editing of the second half (edit_kwargs, :293-298, :520-522, :841-852)
+    "ddpm_scg_edit": dict(dit="small", respacing="4", ddim=False, shape=(1, 4, 128, 16), seed=8,
+                          scg=dict(num_samples=2, pitch_hist=1.0), guidance=_GUIDE_ON, rules=["pitch_hist"],
+                          edit=True, rule_len=512),
+    # DiffCollage CondIndSimple, 3 windows -> latent length 256, per-segment selection dc.base = 128 (:562-592)
+    "dc_simple_base": dict(dit="small", respacing="3", ddim=False, shape=(1, 4, 256, 16), seed=9,
+                           scg=dict(num_samples=2, pitch_hist=1.0, note_density=0.5),
+                           guidance=dict(_GUIDE_ON, dc=dict(base=128)), rules=["pitch_hist", "note_density"],
+                           dc=dict(type="simple", num_img=3)),
+    # DiffCollage CondIndCircle (num_img + 1 windows, scripts/sample_rule.py:127), DDIM eta = 1
+    "dc_circle": dict(dit="small", respacing="3", ddim=True, eta=1.0, shape=(1, 4, 256, 16), seed=10,
+                      scg=dict(num_samples=2, pitch_hist=1.0), guidance=_GUIDE_ON, rules=["pitch_hist"],
+                      dc=dict(type="circle", num_img=3)),
+}
+
+
+def ext_model_kwargs(cfg):
+    B, _, H, _ = cfg["shape"]
+    kw = {"y": torch.ones(B, dtype=torch.long)}
+    kw["rule"] = rule_targets(B, cfg.get("rule_len", H * 8), cfg["rules"])
+    return kw

@@ -97,11 +97,11 @@ def test_conv_resid_and_gn_partials(cuda):
     w = (torch.randn(cout, cin, 3, 3, generator=g) / (cin * 9) ** 0.5).to(cuda)
     bias = torch.randn(cout, generator=g).to(cuda)
     resid = torch.randn(n, H, H, cout, generator=g).to(cuda).half()
-    part = torch.zeros(n * H * H // 32, cout // 4, 2, device=cuda)
+    part = torch.zeros(n * H * H // 128, cout // 4, 2, device=cuda)
     out = _conv(x, _pack(w, 1), bias, cout, 1, resid=resid, gn_part=part)
     ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.half().float(), bias, padding=1).permute(0, 2, 3, 1) + resid.float()
     torch.cuda.synchronize()
     assert (out.float() - ref).abs().max().item() <= 4e-3 * ref.abs().max().item()
-    o = out.float().reshape(n * H * H // 32, 32, cout // 4, 4)
-    assert torch.allclose(part[..., 0], o.sum(dim=(1, 3)), rtol=1e-4, atol=1e-2)
-    assert torch.allclose(part[..., 1], (o * o).sum(dim=(1, 3)), rtol=1e-4, atol=1e-2)
+    o = out.float().reshape(n * H * H // 128, 128, cout // 4, 4)  # partial sums per (128 rows x 4 channels)
+    assert torch.allclose(part[..., 0], o.sum(dim=(1, 3)), rtol=1e-4, atol=3e-2)
+    assert torch.allclose(part[..., 1], (o * o).sum(dim=(1, 3)), rtol=1e-4, atol=3e-2)

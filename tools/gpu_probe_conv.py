@@ -4,8 +4,8 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from rule_guided_music_b200 import _lib
 dev = torch.device("cuda:0")
 case = os.environ.get("CASE", "conv128")
-if case == "conv128":
-    n, H, cin, cout = 64, 128, 128, 128
+if case in ("conv128", "conv64"):
+    n, H, cin, cout = (64, 128, 128, 128) if case == "conv128" else (128, 64, 256, 256)
     x = torch.randn(n, H, H, cin, device=dev).half()
     w = torch.randn(cout * 9 * cin, device=dev).half() * 0.02
     bias = torch.zeros(cout, device=dev)

@@ -216,6 +216,7 @@ def run_b200(args):
     barrier()
     ms_e2e = e2.elapsed_time(e3)
     # ---- per-kernel device times for the roofline (separate pass, events around every launch) ----------------------
+    vae.set_lanes(1)  # serial execution so that each launch's event pair times that launch alone
     _lib.prof_enable(True)
     for _ in range(args.prof_steps):
         x = step(x, k)

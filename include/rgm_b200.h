@@ -63,6 +63,9 @@ typedef struct rgm_vae rgm_vae;
 int rgm_vae_create(rgm_vae** out, int ch, const int* ch_mult_host, int n_levels, int num_res_blocks, int z_channels,
                    int out_ch);
 int rgm_vae_destroy(rgm_vae* h);
+/* 2 (default): consecutive tile chunks alternate between two internal streams so GroupNorm passes overlap convolutions;
+ * 1: strictly serial on the caller's stream (used for per-kernel timing) */
+int rgm_vae_set_lanes(rgm_vae* h, int lanes);
 /* AutoencoderKL.init_from_ckpt (klvae_pedal.py:50-59), one tensor per call; keys "post_quant_conv.*", "decoder.*".
  * Same return convention as rgm_dit_load. */
 int rgm_vae_load(rgm_vae* h, const char* key, const float* src, long long numel, void* stream);

@@ -46,6 +46,7 @@ _SIGNATURES = {
     "rgm_dit_forward": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p],
     "rgm_vae_create": [_HP, c_int, ctypes.POINTER(c_int), c_int, c_int, c_int, c_int],
     "rgm_vae_destroy": [c_void_p],
+    "rgm_vae_set_lanes": [c_void_p, c_int],
     "rgm_vae_load": [c_void_p, c_char_p, c_void_p, c_ll, c_void_p],
     "rgm_vae_decode_latents": [c_void_p, c_void_p, c_float, c_void_p, c_int, c_int, c_int, c_void_p],
     "rgm_rule_pitch_hist": [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p],

@@ -335,10 +335,12 @@ cudaError_t launch_gn_finalize(const float* part, const float* gamma, const floa
 }
 
 // grid = (pixel chunks, images).  A thread owns ONE 8-channel vector position (its GroupNorm coefficients stay in
-// registers) and walks the image's pixels with a stride, four 16-byte loads in flight; a warp covers 512 contiguous
+// registers) and walks the image's pixels with a stride, three 16-byte loads in flight; a warp covers 512 contiguous
 // bytes per load.  One fp16 read and one fp16 write per element.
+// (__launch_bounds__(256, 6) caps the kernel at 42 registers so that one block fits beside a resident GEMM CTA --
+// 320 threads x 168 registers -- and the two VAE lanes really overlap HBM-bound and tensor-bound work on an SM)
 template <int SWISH>
-__global__ void __launch_bounds__(256) gn_apply_kernel(const __half* __restrict__ x, const float2* __restrict__ ab,
+__global__ void __launch_bounds__(256, 6) gn_apply_kernel(const __half* __restrict__ x, const float2* __restrict__ ab,
                                                        __half* __restrict__ y, int HW, int C) {
   const int cv = C >> 3;                       // 8-channel vectors per pixel (16, 32 or 64)
   const int c8 = threadIdx.x % cv;
@@ -377,12 +379,12 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const __half* __restrict_
     return o;
   };
   int p = blockIdx.x * ppb + prow;
-  for (; p + 3 * step < HW; p += 4 * step) {
-    uint4 u[4];
+  for (; p + 2 * step < HW; p += 3 * step) {
+    uint4 u[3];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) u[i] = __ldcs(xin + (long long)(p + i * step) * cv);
+    for (int i = 0; i < 3; ++i) u[i] = __ldcs(xin + (long long)(p + i * step) * cv);
 #pragma unroll
-    for (int i = 0; i < 4; ++i) yout[(long long)(p + i * step) * cv] = apply(u[i]);
+    for (int i = 0; i < 3; ++i) yout[(long long)(p + i * step) * cv] = apply(u[i]);
   }
   for (; p < HW; p += step) yout[(long long)p * cv] = apply(__ldcs(xin + (long long)p * cv));
 }
@@ -403,107 +405,158 @@ cudaError_t launch_gn_apply(const __half* x, const float2* ab, __half* y, int n,
   return done();
 }
 
-// norm_out (GroupNorm apply + swish, model.py:533-535) + conv_out 3x3 C -> out_ch (model.py:536) + assembly of the
-// piano roll (gaussian_diffusion.py:1355), on the CUDA cores: with 3 output channels the tensor-core tile would be
-// 90 % padding and the 9 shifted re-reads of the 128-channel input would dominate.  One block = 16x16 output pixels;
-// the 18x18 halo of the RAW input is loaded once, normalised + activated on the way into shared memory (zero for
-// out-of-image pixels: the conv pads the ACTIVATED tensor), then each thread accumulates its pixel's <= 4 outputs
-// in fp32 with fp32 weights.  Pixel stride in smem is padded by 16 B so the 16-byte loads of a warp's 32 consecutive
-// pixels hit distinct banks.
-__global__ void __launch_bounds__(256) vae_out_kernel(const __half* __restrict__ x, const float2* __restrict__ ab,
+// norm_out (GroupNorm apply + swish, model.py:533-535) + conv_out 3x3 C -> out_ch <= 8 (model.py:536) + assembly of
+// the piano roll (gaussian_diffusion.py:1355) in one kernel.  With 3 output channels a tcgen05 tile would be > 90 %
+// padding and the 9 shifted re-reads of the 128-channel input would dominate, so: one block = 16x16 output pixels; the
+// 18x18 halo of the RAW input is loaded once, normalised + activated on the way into shared memory (zero for
+// out-of-image pixels: the conv pads the ACTIVATED tensor); the 9-tap contraction then runs on warp-level
+// mma.sync m16n8k16 (16 pixels x 8 padded output channels x 16 input channels, fp32 accumulate) with ldmatrix
+// operand loads -- a CUDA-core version of the same loop measured instruction-issue bound at 80 K warp-instructions per
+// block.  Pixel stride in smem is padded by 16 B so ldmatrix rows (consecutive pixels) hit distinct banks.
+__device__ __forceinline__ void ldmatrix_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
+               : "r"(addr));
+}
+__device__ __forceinline__ void mma_16816(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
+                                          uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, "
+      "{%0, %1, %2, %3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+__global__ void __launch_bounds__(512) vae_out_kernel(const __half* __restrict__ x, const float2* __restrict__ ab,
                                                       const float* __restrict__ w, const float* __restrict__ bias,
                                                       float* __restrict__ roll, int C, int out_ch, int tile0, int n_cand,
                                                       int roll_len, int roll_ch) {
-  extern __shared__ uint8_t osm[];
+  extern __shared__ __align__(16) uint8_t osm[];
   const int pstride = C * 2 + 16;                       // bytes per halo pixel
   uint8_t* halo = osm;                                  // [18*18][pstride]
-  float4* wsm = reinterpret_cast<float4*>(osm + ((18 * 18 * pstride + 15) & ~15));  // [9][C] (w0, w1, w2, w3)
-  float2* absm = reinterpret_cast<float2*>(wsm + 9 * C);                             // [C]
+  const int kchunks = C >> 4;                           // 16-channel k-steps
+  uint2* bfrag = reinterpret_cast<uint2*>(osm + ((18 * 18 * pstride + 15) & ~15));  // [9][kchunks][32 lanes] B fragments
+  float2* absm = reinterpret_cast<float2*>(bfrag + 9 * kchunks * 32);              // [C]
   const int img = blockIdx.y;
   const int by = blockIdx.x >> 3, bx = blockIdx.x & 7;  // 8 x 8 blocks of 16 x 16 pixels per 128 x 128 image
-  for (int i = threadIdx.x; i < C; i += 256) absm[i] = ab[(long long)img * C + i];
-  for (int i = threadIdx.x; i < 9 * C; i += 256) {
-    const int tap = i / C, c = i - tap * C;
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    v.x = w[((long long)0 * C + c) * 9 + tap];
-    if (out_ch > 1) v.y = w[((long long)1 * C + c) * 9 + tap];
-    if (out_ch > 2) v.z = w[((long long)2 * C + c) * 9 + tap];
-    if (out_ch > 3) v.w = w[((long long)3 * C + c) * 9 + tap];
-    wsm[i] = v;
+  for (int i = threadIdx.x; i < C; i += 512) absm[i] = ab[(long long)img * C + i];
+  // B fragment of mma.m16n8k16 (col-major k16 x n8): lane l holds W[k = 2*(l%4) + {0,1}][n = l/4] and the same at k + 8;
+  // output channels >= out_ch are zero padding
+  for (int i = threadIdx.x; i < 9 * kchunks * 32; i += 512) {
+    const int l = i & 31, kc = (i >> 5) % kchunks, tap = i / (32 * kchunks);
+    const int n = l >> 2, k0 = kc * 16 + 2 * (l & 3);
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
+    if (n < out_ch) {
+      const float* wp = w + (long long)n * C * 9 + tap;
+      v[0] = wp[(k0) * 9];
+      v[1] = wp[(k0 + 1) * 9];
+      v[2] = wp[(k0 + 8) * 9];
+      v[3] = wp[(k0 + 9) * 9];
+    }
+    __half2 lo = __floats2half2_rn(v[0], v[1]), hi = __floats2half2_rn(v[2], v[3]);
+    bfrag[i] = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
   }
   __syncthreads();
   const int cv = C >> 3;
   const __half* xin = x + (long long)img * 128 * 128 * C;
-  for (int i = threadIdx.x; i < 18 * 18 * cv; i += 256) {
-    const int pix = i / cv, c8 = i - pix * cv;
-    const int hy = pix / 18, hx = pix - hy * 18;
-    const int gy = by * 16 + hy - 1, gx = bx * 16 + hx - 1;
-    uint4 o = make_uint4(0u, 0u, 0u, 0u);
-    if (gy >= 0 && gy < 128 && gx >= 0 && gx < 128) {
-      const uint4 u = __ldg(reinterpret_cast<const uint4*>(xin + ((long long)gy * 128 + gx) * C) + c8);
-      const __half2* h2 = reinterpret_cast<const __half2*>(&u);
-      __half2* o2 = reinterpret_cast<__half2*>(&o);
+  // halo load: four 16-byte global loads in flight per thread before any dependent work.  512 is a multiple of cv, so a
+  // thread always handles the same 8-channel chunk: its GroupNorm coefficients live in registers (reading them from
+  // shared memory per item measured 16-way bank conflicts, 80 % of the kernel's smem wavefronts).
+  const int items = 18 * 18 * cv;
+  const int c8 = threadIdx.x % cv;
+  float ga[8], gb[8];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float2 f = __half22float2(h2[j]);
-        const float2 a0 = absm[c8 * 8 + 2 * j], a1 = absm[c8 * 8 + 2 * j + 1];
-        float v0 = fmaf(a0.x, f.x, a0.y), v1 = fmaf(a1.x, f.y, a1.y);
-        v0 = __fdividef(v0, 1.0f + __expf(-v0));
-        v1 = __fdividef(v1, 1.0f + __expf(-v1));
-        o2[j] = __floats2half2_rn(v0, v1);  // the same fp16 rounding the stand-alone GroupNorm pass applies
-      }
+  for (int j = 0; j < 8; ++j) {
+    const float2 t = absm[c8 * 8 + j];
+    ga[j] = t.x;
+    gb[j] = t.y;
+  }
+  for (int i0 = threadIdx.x; i0 < items; i0 += 4 * 512) {
+    uint4 u[4];
+    bool inside[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int i = i0 + k * 512;
+      const int pix = i / cv;
+      const int hy = pix / 18, hx = pix - hy * 18;
+      const int gy = by * 16 + hy - 1, gx = bx * 16 + hx - 1;
+      inside[k] = i < items && gy >= 0 && gy < 128 && gx >= 0 && gx < 128;
+      u[k] = make_uint4(0u, 0u, 0u, 0u);
+      if (inside[k]) u[k] = __ldg(reinterpret_cast<const uint4*>(xin + ((long long)gy * 128 + gx) * C) + c8);
     }
-    *reinterpret_cast<uint4*>(halo + pix * pstride + c8 * 16) = o;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int i = i0 + k * 512;
+      if (i >= items) break;
+      const int pix = i / cv;
+      uint4 o = make_uint4(0u, 0u, 0u, 0u);
+      if (inside[k]) {
+        const __half2* h2 = reinterpret_cast<const __half2*>(&u[k]);
+        __half2* o2 = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 f = __half22float2(h2[j]);
+          float v0 = fmaf(ga[2 * j], f.x, gb[2 * j]), v1 = fmaf(ga[2 * j + 1], f.y, gb[2 * j + 1]);
+          v0 = __fdividef(v0, 1.0f + __expf(-v0));
+          v1 = __fdividef(v1, 1.0f + __expf(-v1));
+          o2[j] = __floats2half2_rn(v0, v1);  // the same fp16 rounding the stand-alone GroupNorm pass applies
+        }
+      }
+      *reinterpret_cast<uint4*>(halo + pix * pstride + c8 * 16) = o;
+    }
   }
   __syncthreads();
-  const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
-  float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
+  // contraction: warp w (of 16) owns output row w of the tile (one m16 tile of 16 consecutive pixels)
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  const uint32_t halo_s = static_cast<uint32_t>(__cvta_generic_to_shared(halo));
+  // ldmatrix.x4 address of this lane: matrix m = lane / 8 covers pixels 8*(m & 1) .. +7 and channels 8*(m >> 1) .. +7
+  const int lm_pix = (lane & 7) + 8 * ((lane >> 3) & 1);
+  const int lm_coff = (lane >> 4) * 16;  // bytes
 #pragma unroll 1
   for (int tap = 0; tap < 9; ++tap) {
     const int dy = tap / 3, dx = tap - dy * 3;
-    const uint8_t* prow = halo + ((ty + dy) * 18 + tx + dx) * pstride;
-    const float4* wt = wsm + tap * C;
+    const uint2* bt = bfrag + (tap * kchunks) * 32 + lane;
+    const uint32_t a_row0 = halo_s + ((warp + dy) * 18 + dx + lm_pix) * pstride + lm_coff;
 #pragma unroll 4
-    for (int c8 = 0; c8 < cv; ++c8) {
-      const uint4 u = *reinterpret_cast<const uint4*>(prow + c8 * 16);
-      const __half2* h2 = reinterpret_cast<const __half2*>(&u);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float2 f = __half22float2(h2[j]);
-        const float4 w0 = wt[c8 * 8 + 2 * j], w1 = wt[c8 * 8 + 2 * j + 1];
-        acc0 = fmaf(f.x, w0.x, acc0);
-        acc1 = fmaf(f.x, w0.y, acc1);
-        acc2 = fmaf(f.x, w0.z, acc2);
-        acc3 = fmaf(f.x, w0.w, acc3);
-        acc0 = fmaf(f.y, w1.x, acc0);
-        acc1 = fmaf(f.y, w1.y, acc1);
-        acc2 = fmaf(f.y, w1.z, acc2);
-        acc3 = fmaf(f.y, w1.w, acc3);
-      }
+    for (int kc = 0; kc < kchunks; ++kc) {
+      const uint2 b = bt[kc * 32];
+      uint32_t a0, a1, a2, a3;
+      ldmatrix_x4(a_row0 + kc * 32, a0, a1, a2, a3);
+      mma_16816(acc, a0, a1, a2, a3, b.x, b.y);
     }
   }
+  // accumulator layout: c0,c1 = (pixel lane/4, channels 2*(lane%4) + {0,1}); c2,c3 = (pixel lane/4 + 8, same channels)
   const int g = tile0 + img;  // global tile index, tile-major: g = k * n_cand + cand
   const int kt = g / n_cand, cand = g - kt * n_cand;
-  const int h = by * 16 + ty, wcol = kt * 128 + bx * 16 + tx;
-  const float accs[4] = {acc0, acc1, acc2, acc3};
+  const int ch0 = 2 * (lane & 3);
+  const int h = by * 16 + warp;
+  const int wcol = kt * 128 + bx * 16 + (lane >> 2);
 #pragma unroll
-  for (int ch = 0; ch < 4; ++ch)
-    if (ch < roll_ch) roll[(((long long)cand * roll_ch + ch) * 128 + h) * roll_len + wcol] = accs[ch] + bias[ch];
+  for (int j = 0; j < 2; ++j) {
+    const int ch = ch0 + j;
+    if (ch < roll_ch) {
+      float* dst = roll + (((long long)cand * roll_ch + ch) * 128 + h) * roll_len + wcol;
+      dst[0] = acc[j] + bias[ch];
+      dst[8] = acc[2 + j] + bias[ch];
+    }
+  }
 }
 
 cudaError_t launch_vae_out(const __half* x, const float2* ab, const float* w, const float* bias, float* roll, int n,
                            int C, int out_ch, int tile0, int n_cand, int roll_len, int roll_ch, cudaStream_t s) {
-  if (C % 8 != 0 || out_ch < 1 || out_ch > 4 || roll_ch > out_ch) return cudaErrorInvalidValue;
-  const size_t smem = ((18 * 18 * (C * 2 + 16) + 15) & ~15) + (size_t)9 * C * sizeof(float4) + (size_t)C * sizeof(float2);
+  if (C % 16 != 0 || 512 % (C / 8) != 0 || out_ch < 1 || out_ch > 8 || roll_ch > out_ch) return cudaErrorInvalidValue;
+  const size_t smem = ((18 * 18 * (C * 2 + 16) + 15) & ~15) + (size_t)9 * (C / 16) * 32 * sizeof(uint2) +
+                      (size_t)C * sizeof(float2);
   static size_t smem_set = 0;
   if (smem > smem_set) {
     cudaError_t e = cudaFuncSetAttribute(vae_out_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     smem_set = smem;
   }
-  ProfScope prof("vae_out(norm+swish+conv_out+roll)", 2.0 * n * 16384.0 * out_ch * 9.0 * C, 2.0 * n * 16384.0 * 4 * 9.0 * C,
+  ProfScope prof("vae_out(norm+swish+conv_out+roll)", 2.0 * n * 16384.0 * out_ch * 9.0 * C, 2.0 * n * 16384.0 * 8 * 9.0 * C,
                  (double)n * 16384.0 * (C * 2.0 + roll_ch * 4.0), s);
-  vae_out_kernel<<<dim3(64, n), 256, smem, s>>>(x, ab, w, bias, roll, C, out_ch, tile0, n_cand, roll_len, roll_ch);
+  vae_out_kernel<<<dim3(64, n), 512, smem, s>>>(x, ab, w, bias, roll, C, out_ch, tile0, n_cand, roll_len, roll_ch);
   return done();
 }
 

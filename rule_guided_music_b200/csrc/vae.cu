@@ -385,7 +385,7 @@ int rgm_vae_create(rgm_vae** out, int ch, const int* ch_mult, int n_levels, int 
   if (rgm_check_device()) return -1;
   if (!out || !ch_mult || n_levels < 1 || n_levels > 8) return set_error("rgm_vae_create: bad arguments");
   if (z_channels != 4) return set_error("rgm_vae_create: the fused stem is written for z_channels = 4");
-  if (out_ch > 4) return set_error("rgm_vae_create: out_ch > 4 (the fused conv_out kernel keeps <= 4 accumulators)");
+  if (out_ch > 8) return set_error("rgm_vae_create: out_ch > 8 (the fused conv_out kernel pads the output channels to 8)");
   Vae* m = new Vae();
   m->ch = ch;
   m->n_levels = n_levels;
@@ -409,6 +409,12 @@ int rgm_vae_create(rgm_vae** out, int ch, const int* ch_mult, int n_levels, int 
     return -1;
   }
   *out = reinterpret_cast<rgm_vae*>(m);
+  return 0;
+}
+
+int rgm_vae_set_lanes(rgm_vae* h, int lanes) {
+  if (!h) return set_error("rgm_vae_set_lanes: null handle");
+  reinterpret_cast<Vae*>(h)->n_lanes = lanes >= 2 ? 2 : 1;
   return 0;
 }
 

@@ -91,6 +91,10 @@ class AutoencoderKL:
             torch.cuda.current_stream().synchronize()
         return unexpected
 
+    def set_lanes(self, lanes):
+        """2 = overlap GroupNorm passes of one tile chunk with the convolutions of the next (default), 1 = serial."""
+        _lib.call("rgm_vae_set_lanes", self._h, int(lanes))
+
     def _destroy(self):
         if self._h is not None:
             _lib.lib().rgm_vae_destroy(self._h)

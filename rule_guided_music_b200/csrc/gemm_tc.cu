@@ -130,6 +130,30 @@ cudaError_t launch_sw(const CUtensorMap& mx, const CUtensorMap& mw, const GemmPa
   return cudaGetLastError();
 }
 
+template <int EPI>
+cudaError_t launch_sw2(const CUtensorMap& mx, const CUtensorMap& mw, const GemmParams& p, int grid,
+                       cudaStream_t stream) {
+  static bool attr_set = false;
+  auto kern = gemm_sw2_kernel<EPI>;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SW2_SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  kern<<<grid, GEMM_THREADS, SW2_SMEM_BYTES, stream>>>(mx, mw, p);  // 2-CTA clusters (__cluster_dims__)
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return cudaGetLastError();
+}
+
+bool pair_mode_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("RGM_GEMM_PAIR");
+    v = (e && atoi(e) == 0) ? 0 : 1;
+  }
+  return v != 0;
+}
+
 }  // namespace
 
 unsigned long long gemm_launch_count() { return g_launches.load(); }
@@ -239,8 +263,25 @@ cudaError_t launch_gemm(const GemmDesc& d, cudaStream_t stream, std::string* err
     if (!make_map(&mb, d.B, 3, dims, strides, box, err)) return cudaErrorInvalidValue;
   }
 
-  const long long total = (long long)p.num_m_tiles * p.num_n_tiles * p.num_par;
-  const int grid = (int)(total < device_sm_count() ? total : device_sm_count());
+  // CTA pairs (gemm_sw2_kernel) when there are at least two feature tiles and enough pair tiles to fill the machine
+  const long long pair_tiles = (long long)p.num_m_tiles * ((p.num_n_tiles + 1) / 2) * p.num_par;
+  const bool pair = sw && pair_mode_enabled() && p.num_n_tiles >= 2 && pair_tiles >= device_sm_count() / 2;
+  CUtensorMap ma2;
+  if (pair) {
+    // this CTA's half of the 256-row activation box: half the image rows, or 128 of the 256 linear rows
+    cuuint64_t wdim = (cuuint64_t)d.W;
+    if (d.H == 1 && d.n_img == 1 && d.a_rows > d.W) wdim = (cuuint64_t)d.a_rows;
+    cuuint64_t dims[4] = {(cuuint64_t)d.C, wdim, (cuuint64_t)d.H, (cuuint64_t)d.n_img};
+    cuuint64_t strides[3] = {(cuuint64_t)d.lda * 2, wdim * d.lda * 2, (cuuint64_t)d.H * wdim * d.lda * 2};
+    cuuint32_t box[4] = {GEMM_BLOCK_K, (cuuint32_t)(bh > 1 ? bw : bw / 2), (cuuint32_t)(bh > 1 ? bh / 2 : 1), 1};
+    if (!make_map(&ma2, d.A, 4, dims, strides, box, err)) return cudaErrorInvalidValue;
+  }
+  const long long total = pair ? pair_tiles : (long long)p.num_m_tiles * p.num_n_tiles * p.num_par;
+  int grid = (int)(total < device_sm_count() ? total : device_sm_count());
+  if (pair) {
+    const int max_pairs = device_sm_count() / 2;
+    grid = 2 * (int)(total < max_pairs ? total : max_pairs);
+  }
   if (grid <= 0) return cudaSuccess;
 
   // profiling label: conv kind, K, N and epilogue identify the layer family; flops_alg counts the reference's
@@ -252,11 +293,18 @@ cudaError_t launch_gemm(const GemmDesc& d, cudaStream_t stream, std::string* err
   const double f_alg = d.conv == CONV_UP2 ? 2.0 * rows * d.N * 9.0 * d.C : f_exec;
   if (g_prof_on.load(std::memory_order_relaxed))
     snprintf(pname, sizeof pname, "gemm_tc conv%d K%d N%d epi%d %s", d.conv, (int)Kexec, d.N, d.epi,
-             sw ? "f128xr256" : "r128xf32");
+             pair ? "f256xr256 pair" : (sw ? "f128xr256" : "r128xf32"));
   ProfScope prof(pname, f_alg, f_exec, 0.0, stream);
 
   cudaError_t st = cudaErrorInvalidValue;
-  if (sw) {
+  if (pair) {
+    switch (d.epi) {
+      case EPI_F16: st = launch_sw2<EPI_F16>(ma2, mb, p, grid, stream); break;
+      case EPI_F32: st = launch_sw2<EPI_F32>(ma2, mb, p, grid, stream); break;
+      case EPI_GATE_RESID: st = launch_sw2<EPI_GATE_RESID>(ma2, mb, p, grid, stream); break;
+      default: st = launch_sw2<EPI_QKV_ROPE>(ma2, mb, p, grid, stream); break;
+    }
+  } else if (sw) {
     switch (d.epi) {
       case EPI_F16: st = launch_sw<EPI_F16>(ma, mb, p, grid, stream); break;
       case EPI_F32: st = launch_sw<EPI_F32>(ma, mb, p, grid, stream); break;

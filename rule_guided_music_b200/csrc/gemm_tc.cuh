@@ -569,6 +569,85 @@ constexpr uint32_t SW_W_BYTES = SW_FEATS * GEMM_BLOCK_K * 2;  // 16 KB
 constexpr uint32_t SW_X_BYTES = SW_ROWS * GEMM_BLOCK_K * 2;   // 32 KB
 constexpr size_t SW_SMEM_BYTES = 1024 + SW_STAGES * (SW_W_BYTES + SW_X_BYTES) + 256;
 
+// Epilogue of one feature-major tile for one epilogue warp: TMEM lanes quad*32.. = 32 features, TMEM columns
+// rhalf*128.. = 128 of the tile's 256 rows, walked in rounds of 32 rows.
+template <int EPI>
+__device__ __forceinline__ void sw_epilogue_tile(const GemmParams& p, uint32_t tmem_acc, int m_tile, int n_tile,
+                                                 int par, int quad, int rhalf, int lane) {
+  const uint32_t taddr = tmem_acc + (static_cast<uint32_t>(quad * 32) << 16) + rhalf * 128;
+  const int n = n_tile * SW_FEATS + quad * 32 + lane;  // this thread's output feature
+  float gs = 0.f, gq = 0.f;  // GroupNorm sum / sum of squares of feature n over this warp's 128 rows
+#pragma unroll 1
+  for (int c = 0; c < 128; c += 32) {
+    const int row0 = m_tile * SW_ROWS + rhalf * 128 + c;
+    if (row0 >= p.M) break;
+    uint32_t r[32];
+    tmem_ld_32x32(taddr + c, r);
+    tmem_ld_wait();
+    if constexpr (EPI == EPI_QKV_ROPE) {
+      const int D = p.epi.heads * p.epi.dh;
+      if (n_tile * SW_FEATS + quad * 32 >= 2 * D) {
+        // V features -> V^T [B, heads, dh, T] (the K-major B operand of the P.V MMA): this thread holds 32
+        // consecutive tokens of one (head, d) row = 64 contiguous bytes
+        const EpiParams& e = p.epi;
+        const int rem = n - 2 * D;
+        const int head = rem / e.dh, d = rem - head * e.dh;
+        const int b0 = row0 / e.T, tok0 = row0 - b0 * e.T;
+        const float bias = __ldg(e.bias + n);
+        uint4 pk[4];
+        __half2* h2 = reinterpret_cast<__half2*>(pk);
+#pragma unroll
+        for (int j = 0; j < 32; j += 2)
+          h2[j >> 1] = __floats2half2_rn(__uint_as_float(r[j]) + bias, __uint_as_float(r[j + 1]) + bias);
+        __half* dst = e.v + (((long long)b0 * e.heads + head) * e.dh + d) * e.T + tok0;
+        if (row0 + 32 <= p.M) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) reinterpret_cast<uint4*>(dst)[i] = pk[i];
+        } else {
+          const __half* hv = reinterpret_cast<const __half*>(pk);
+          for (int j = 0; j < p.M - row0; ++j) dst[j] = hv[j];
+        }
+        continue;
+      }
+    }
+    float val[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) val[j] = __uint_as_float(r[j]);
+    // destination rows (see epilogue_cols_core)
+    const int row = row0 + lane;
+    int orow = row < p.M ? row : -1;
+    bool uniform_rows = row0 + 32 <= p.M;
+    int orow0 = row0, orow_step = 1;
+    if (p.epi.up2) {
+      const int hw = p.epi.upH * p.epi.upW;
+      if (orow >= 0) {
+        const int im = row / hw, rem = row - im * hw;
+        const int h = rem / p.epi.upW, w = rem - h * p.epi.upW;
+        orow = (im * (2 * p.epi.upH) + (2 * h + (par >> 1))) * (2 * p.epi.upW) + (2 * w + (par & 1));
+      }
+      uniform_rows = uniform_rows && (p.epi.upW % 32 == 0);
+      orow0 = __shfl_sync(0xffffffffu, orow, 0);
+      orow_step = 2;
+    }
+    epilogue_cols_core<EPI, false>(p, val, 0u, lane, row0, orow, uniform_rows, orow0, orow_step, n, par, gs, gq);
+  }
+  if constexpr (EPI == EPI_F16) {
+    const int rbase = m_tile * SW_ROWS + rhalf * 128;
+    if (p.epi.gn_part != nullptr && rbase < p.M) {
+      // GroupNorm partials per (128 rows x 4 channels), no atomics (deterministic): lanes 4k..4k+3 hold one quad;
+      // gn_finalize_kernel folds quads into groups and sums an image's slots in a fixed order
+      gs += __shfl_xor_sync(0xffffffffu, gs, 1);
+      gq += __shfl_xor_sync(0xffffffffu, gq, 1);
+      gs += __shfl_xor_sync(0xffffffffu, gs, 2);
+      gq += __shfl_xor_sync(0xffffffffu, gq, 2);
+      if ((lane & 3) == 0) {
+        const long long slot = (long long)par * p.slots_per_par + (rbase >> 7);
+        reinterpret_cast<float2*>(p.epi.gn_part)[slot * (p.N >> 2) + (n >> 2)] = make_float2(gs, gq);
+      }
+    }
+  }
+}
+
 template <int EPI>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_sw_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
@@ -694,78 +773,7 @@ gemm_sw_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       if (p.trace && blockIdx.x == 0 && warp == 2 && lane == 0) p.trace[(t / gridDim.x) * 8 + 4] = clock64();
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * SW_ROWS + rhalf * 128;
-      const int n = n_tile * SW_FEATS + quad * 32 + lane;  // this thread's output feature
-      float gs = 0.f, gq = 0.f;  // GroupNorm sum / sum of squares of feature n over this warp's 128 rows
-#pragma unroll 1
-      for (int c = 0; c < 128; c += 32) {
-        const int row0 = m_tile * SW_ROWS + rhalf * 128 + c;
-        if (row0 >= p.M) break;
-        uint32_t r[32];
-        tmem_ld_32x32(taddr + c, r);
-        tmem_ld_wait();
-        if constexpr (EPI == EPI_QKV_ROPE) {
-          const int D = p.epi.heads * p.epi.dh;
-          if (n_tile * SW_FEATS + quad * 32 >= 2 * D) {
-            // V features -> V^T [B, heads, dh, T] (the K-major B operand of the P.V MMA): this thread holds 32
-            // consecutive tokens of one (head, d) row = 64 contiguous bytes
-            const EpiParams& e = p.epi;
-            const int rem = n - 2 * D;
-            const int head = rem / e.dh, d = rem - head * e.dh;
-            const int b0 = row0 / e.T, tok0 = row0 - b0 * e.T;
-            const float bias = __ldg(e.bias + n);
-            uint4 pk[4];
-            __half2* h2 = reinterpret_cast<__half2*>(pk);
-#pragma unroll
-            for (int j = 0; j < 32; j += 2)
-              h2[j >> 1] = __floats2half2_rn(__uint_as_float(r[j]) + bias, __uint_as_float(r[j + 1]) + bias);
-            __half* dst = e.v + (((long long)b0 * e.heads + head) * e.dh + d) * e.T + tok0;
-            if (row0 + 32 <= p.M) {
-#pragma unroll
-              for (int i = 0; i < 4; ++i) reinterpret_cast<uint4*>(dst)[i] = pk[i];
-            } else {
-              const __half* hv = reinterpret_cast<const __half*>(pk);
-              for (int j = 0; j < p.M - row0; ++j) dst[j] = hv[j];
-            }
-            continue;
-          }
-        }
-        float val[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) val[j] = __uint_as_float(r[j]);
-        // destination rows (see epilogue_cols_core)
-        const int row = row0 + lane;
-        int orow = row < p.M ? row : -1;
-        bool uniform_rows = row0 + 32 <= p.M;
-        int orow0 = row0, orow_step = 1;
-        if (p.epi.up2) {
-          const int hw = p.epi.upH * p.epi.upW;
-          if (orow >= 0) {
-            const int im = row / hw, rem = row - im * hw;
-            const int h = rem / p.epi.upW, w = rem - h * p.epi.upW;
-            orow = (im * (2 * p.epi.upH) + (2 * h + (par >> 1))) * (2 * p.epi.upW) + (2 * w + (par & 1));
-          }
-          uniform_rows = uniform_rows && (p.epi.upW % 32 == 0);
-          orow0 = __shfl_sync(0xffffffffu, orow, 0);
-          orow_step = 2;
-        }
-        epilogue_cols_core<EPI, false>(p, val, 0u, lane, row0, orow, uniform_rows, orow0, orow_step, n, par, gs, gq);
-      }
-      if constexpr (EPI == EPI_F16) {
-        const int rbase = m_tile * SW_ROWS + rhalf * 128;
-        if (p.epi.gn_part != nullptr && rbase < p.M) {
-          // GroupNorm partials per (128 rows x 4 channels), no atomics (deterministic): lanes 4k..4k+3 hold one quad;
-          // gn_finalize_kernel folds quads into groups and sums an image's slots in a fixed order
-          gs += __shfl_xor_sync(0xffffffffu, gs, 1);
-          gq += __shfl_xor_sync(0xffffffffu, gq, 1);
-          gs += __shfl_xor_sync(0xffffffffu, gs, 2);
-          gq += __shfl_xor_sync(0xffffffffu, gq, 2);
-          if ((lane & 3) == 0) {
-            const long long slot = (long long)par * p.slots_per_par + (rbase >> 7);
-            reinterpret_cast<float2*>(p.epi.gn_part)[slot * (p.N >> 2) + (n >> 2)] = make_float2(gs, gq);
-          }
-        }
-      }
+      sw_epilogue_tile<EPI>(p, tmem_base + acc * SW_ROWS, m_tile, n_tile, par, quad, rhalf, lane);
       tc_fence_before();
       __syncwarp();
       if (p.trace && blockIdx.x == 0 && warp == 2 && lane == 0) p.trace[(t / gridDim.x) * 8 + 5] = clock64();
@@ -782,6 +790,174 @@ gemm_sw_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ================================================================================================================
+// CTA-pair variant of the feature-major kernel: a 2-CTA cluster computes 256 features x 256 rows with
+// tcgen05.mma.cta_group::2.  CTA r of the pair owns features [128 r, 128 r + 128) of the pair tile (its half of the M
+// dimension: its own weight tile, its own TMEM lanes, its own epilogue) and loads rows [128 r, 128 r + 128) of the
+// activation tile (its half of the shared B operand).  Per CTA and k-block that is 16 KB + 16 KB instead of
+// 16 KB + 32 KB: a third less L2 -> shared-memory traffic and six pipeline stages instead of four in the same
+// 192 KB, which is what the short-K (K = 1152) GEMMs were starved of (ncu: tensor pipe 63 % active, L2 41 % busy).
+// ================================================================================================================
+constexpr int SW2_STAGES = 6;
+constexpr uint32_t SW2_W_BYTES = SW_FEATS * GEMM_BLOCK_K * 2;       // 16 KB: this CTA's 128 features
+constexpr uint32_t SW2_X_BYTES = (SW_ROWS / 2) * GEMM_BLOCK_K * 2;  // 16 KB: this CTA's 128 of the 256 rows
+constexpr size_t SW2_SMEM_BYTES = 1024 + SW2_STAGES * (SW2_W_BYTES + SW2_X_BYTES) + 256;
+
+template <int EPI>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
+gemm_sw2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
+                const __grid_constant__ GemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_w = smem;
+  uint8_t* smem_x = smem + SW2_STAGES * SW2_W_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_x + SW2_STAGES * SW2_X_BYTES);  // used in the leader only
+  uint64_t* empty_bar = full_bar + SW2_STAGES;
+  uint64_t* tmem_full = empty_bar + SW2_STAGES;
+  uint64_t* tmem_empty = tmem_full + 2;                                                   // used in the leader only
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_x);
+    tma_prefetch_desc(&tmap_w);
+    for (int i = 0; i < SW2_STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], 2 * GEMM_EPI_WARPS);  // the epilogue warps of both CTAs
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc_pair(tmem_slot, 512);
+    tmem_relinquish_pair();
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // pair tiles: (row tile, PAIR of feature tiles); an odd last feature tile is paired with out-of-range weight rows
+  // (TMA zero-fill) whose epilogue is skipped
+  const int pairs_n = (p.num_n_tiles + 1) >> 1;
+  const int tiles_mn = p.num_m_tiles * pairs_n;
+  const int total_tiles = tiles_mn * p.num_par;
+  const int num_kb = p.num_taps * p.kb_per_tap;
+  const int pair_id = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
+  const int half_h = p.bh >> 1;  // images: this CTA's rows of the pixel box; 0 for linear layers (H == 1)
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = pair_id; t < total_tiles; t += num_pairs) {
+        const int par = t / tiles_mn;
+        const int tt = t - par * tiles_mn;
+        const int m_tile = tt / pairs_n;
+        const int n_tile = 2 * (tt - m_tile * pairs_n) + (int)rank;
+        const int img = m_tile / p.tiles_per_img;
+        const int rr = m_tile - img * p.tiles_per_img;
+        int h0 = (rr / p.tiles_per_row) * p.bh;
+        int w0 = (rr % p.tiles_per_row) * p.bw;
+        if (half_h > 0) h0 += (int)rank * half_h;   // lower / upper half of the pixel box
+        else w0 += (int)rank * (SW_ROWS / 2);       // linear layer: second 128 rows
+        const int wrow = par * p.N + n_tile * SW_FEATS;
+        const int bz = p.b_batched ? img : 0;
+        if (p.trace && blockIdx.x == 0) p.trace[(t / num_pairs) * 8 + 0] = clock64();
+        for (int tap = 0; tap < p.num_taps; ++tap) {
+          const int dy = p.tap_dy[par][tap], dx = p.tap_dx[par][tap];
+          for (int kc = 0; kc < p.kb_per_tap; ++kc) {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * (SW2_W_BYTES + SW2_X_BYTES));
+            tma_load_4d_pair(smem_x + stage * SW2_X_BYTES, &tmap_x, &full_bar[stage], kc * GEMM_BLOCK_K, w0 + dx,
+                             h0 + dy, img);
+            tma_load_3d_pair(smem_w + stage * SW2_W_BYTES, &tmap_w, &full_bar[stage],
+                             (tap * p.kb_per_tap + kc) * GEMM_BLOCK_K, wrow, bz);
+            if (++stage == SW2_STAGES) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && rank == 0) {
+      constexpr uint32_t idesc = umma_idesc_f16(2 * SW_FEATS, SW_ROWS);  // M = 256 over the pair, N = 256
+      int stage = 0, acc = 0;
+      uint32_t phase = 0, acc_phase = 0;
+      for (int t = pair_id; t < total_tiles; t += num_pairs) {
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        if (p.trace && blockIdx.x == 0) p.trace[(t / num_pairs) * 8 + 1] = clock64();
+        const uint32_t d_tmem = tmem_base + acc * SW_ROWS;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          if (kb == 0 && p.trace && blockIdx.x == 0) p.trace[(t / num_pairs) * 8 + 2] = clock64();
+          const uint64_t wdesc = umma_desc_sw128(smem_w + stage * SW2_W_BYTES);
+          const uint64_t xdesc = umma_desc_sw128(smem_x + stage * SW2_X_BYTES);
+#pragma unroll
+          for (int k = 0; k < GEMM_BLOCK_K / 16; ++k)
+            umma_f16_pair(d_tmem, wdesc + 2 * k, xdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          umma_commit_pair(&empty_bar[stage]);  // frees this stage in BOTH CTAs
+          if (++stage == SW2_STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit_pair(&tmem_full[acc]);  // accumulators of both CTAs complete
+        if (p.trace && blockIdx.x == 0) p.trace[(t / num_pairs) * 8 + 3] = clock64();
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
+      }
+    }
+  } else {
+    const int ew = warp - 2;
+    const int quad = warp & 3;
+    const int rhalf = ew >> 2;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int t = pair_id; t < total_tiles; t += num_pairs) {
+      const int par = t / tiles_mn;
+      const int tt = t - par * tiles_mn;
+      const int m_tile = tt / pairs_n;
+      const int n_tile = 2 * (tt - m_tile * pairs_n) + (int)rank;
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      if (p.trace && blockIdx.x == 0 && warp == 2 && lane == 0) p.trace[(t / num_pairs) * 8 + 4] = clock64();
+      if (n_tile < p.num_n_tiles)
+        sw_epilogue_tile<EPI>(p, tmem_base + acc * SW_ROWS, m_tile, n_tile, par, quad, rhalf, lane);
+      tc_fence_before();
+      __syncwarp();
+      if (p.trace && blockIdx.x == 0 && warp == 2 && lane == 0) p.trace[(t / num_pairs) * 8 + 5] = clock64();
+      if (lane == 0) {
+        if (rank == 0) mbar_arrive(&tmem_empty[acc]);
+        else mbar_arrive_remote(&tmem_empty[acc], 0);
+      }
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_pair(tmem_base, 512);
   }
 }
 

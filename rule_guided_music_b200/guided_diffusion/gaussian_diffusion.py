@@ -30,6 +30,7 @@ import numpy as np
 import torch as th
 
 from .. import _lib
+from . import dist_util
 from ..music_rule_guidance import music_rules as _mr
 from ..music_rule_guidance.rule_maps import FUNC_DICT, LOSS_DICT, NATIVE_LOSS_KIND
 
@@ -123,6 +124,11 @@ _TABLES = ("betas", "alphas_cumprod", "alphas_cumprod_prev", "sqrt_alphas_cumpro
            "posterior_log_variance_clipped", "posterior_mean_coef1", "posterior_mean_coef2")
 
 
+class _StepGraph:
+    """One captured step: static input buffers, the graph, and the tensors it leaves its results in."""
+    __slots__ = ("graph", "x", "t", "out", "launches")
+
+
 class GaussianDiffusion:
     """reference :123-189 (constructor and tables) + the sampling methods."""
 
@@ -155,6 +161,9 @@ class GaussianDiffusion:
         self.log_probs, self.each_loss = [], {}
         # debugging / test hook: when set to a list, every SCG decision appends (total_log_prob [N, B], chosen index [B])
         self._trace = None
+        # CUDA-graph replay of whole steps (enable_cuda_graphs): signature -> _StepGraph
+        self._graphs_on = False
+        self._graphs = {}
 
     # ---- device-resident tables ----------------------------------------------------------------------------------
     def _tables(self, device):
@@ -321,7 +330,9 @@ class GaussianDiffusion:
 
     def scg_sample(self, model, t, mean_pred, g_coeff, embed_model, scale_factor, model_kwargs=None, scg_kwargs=None,
                    edit_kwargs=None, dc_kwargs=None, record=False, record_freq=100):
-        """Fan each sample out to N candidate x_{t-1}, score their decoded x0 with the rules, keep the best."""
+        """Fan each sample out to N candidate x_{t-1}, score their decoded x0 with the rules, keep the best.
+        With dist_util.shard_candidates() on, this rank fans out, denoises, decodes and scores only its contiguous
+        share of the N candidates and the ranks exchange their per-sample winners once (dist_util.first_max_over_ranks)."""
         N = int(scg_kwargs["num_samples"])
         B = mean_pred.shape[0]
         dev = mean_pred.device
@@ -331,11 +342,18 @@ class GaussianDiffusion:
         # g_coeff is exp(0.5*log_variance) or sigma expanded to x's shape: one value per sample
         g = g_coeff.reshape(B, -1)[:, 0].contiguous().float()
         noise = th.randn(N, *mean_pred.shape, device=dev, dtype=th.float32)  # same stream as randn_like(sample)
-        cand = th.empty(N * B, *mean_pred.shape[1:], device=dev, dtype=th.float32)
-        _lib.call("rgm_scg_fanout", _lib.ptr(mean_c), _lib.ptr(g), _lib.ptr(noise), _lib.ptr(cand), N, B, elems, stream)
+        shard = dist_util.candidate_sharding()
+        n0, n1 = (0, N) if shard is None else dist_util.shard_range(N, shard[0], shard[1])
+        Nl = n1 - n0  # candidates per sample on this rank
+        if shard is not None:
+            noise = noise[n0:n1].contiguous()  # every rank drew the same N rows; this one keeps rows n0..n1
+        if Nl == 0:  # more ranks than candidates: nothing to offer, but take part in the exchange
+            return self._select(None, None, 0, B, mean_c, n0, shard, record, t, None)
+        cand = th.empty(Nl * B, *mean_pred.shape[1:], device=dev, dtype=th.float32)
+        _lib.call("rgm_scg_fanout", _lib.ptr(mean_c), _lib.ptr(g), _lib.ptr(noise), _lib.ptr(cand), Nl, B, elems, stream)
         del noise
-        t_rep = t.repeat(N)
-        eps = model(cand, self._scale_timesteps(t_rep), y=model_kwargs["y"].repeat(N))
+        t_rep = t.repeat(Nl)
+        eps = model(cand, self._scale_timesteps(t_rep), y=model_kwargs["y"].repeat(Nl))
         if eps.shape[1] != cand.shape[1]:  # learn_sigma models: the mean half (reference splits in p_mean_variance only;
             eps = eps[:, :cand.shape[1]]   # scg_sample would fail its shape assert there)
         tab = self._tables(dev)
@@ -343,7 +361,7 @@ class GaussianDiffusion:
         c = tab["sqrt_recipm1_alphas_cumprod"][t_rep].contiguous()
         x0 = th.empty_like(cand)
         _lib.call("rgm_x0_from_eps", _lib.ptr(cand), _lib.ptr(eps.contiguous()), _lib.ptr(a), _lib.ptr(c), _lib.ptr(x0),
-                  N * B, elems, 0, stream)
+                  Nl * B, elems, 0, stream)
         del eps
         if edit_kwargs is not None:
             x0 = x0[:, :, edit_kwargs["l_start"]:edit_kwargs["l_end"], :].contiguous()
@@ -357,18 +375,10 @@ class GaussianDiffusion:
             roll = x0
         del x0
 
-        cand_v = cand.view(N, B, *mean_pred.shape[1:])
-        idx = th.empty(B, device=dev, dtype=th.int64)
+        cand_v = cand.view(Nl, B, *mean_pred.shape[1:])
         if dc_kwargs is None or getattr(dc_kwargs, "base", 0) <= 0:
-            total, each = self._score_candidates(roll, model_kwargs, scg_kwargs, N, B)
-            sample = th.empty_like(mean_c)
-            _lib.call("rgm_scg_select", _lib.ptr(total), _lib.ptr(cand), _lib.ptr(sample), _lib.ptr(idx), N, B, elems,
-                      stream)
-            if self._trace is not None:
-                self._trace.append((total.view(N, B).clone(), idx.clone()))
-            if record:
-                self._record(t, total, idx, each, N, B)
-            return sample
+            total, each = self._score_candidates(roll, model_kwargs, scg_kwargs, Nl, B)
+            return self._select(total, cand, Nl, B, mean_c, n0, shard, record, t, each)
         # per-segment selection for long sequences (reference :562-592)
         base = int(dc_kwargs.base)
         total_length = roll.shape[-1]
@@ -387,15 +397,36 @@ class GaussianDiffusion:
                     return target[:, i * rule_base: min((i + 1) * rule_base, target.shape[-1])]
                 return target
 
-            total, _ = self._score_candidates(roll_cur, model_kwargs, scg_kwargs, N, B, seg=seg)
+            total, _ = self._score_candidates(roll_cur, model_kwargs, scg_kwargs, Nl, B, seg=seg)
             seg_cand = cand_v[:, :, :, start // 8: end // 8].contiguous()
-            seg_out = th.empty(B, *seg_cand.shape[2:], device=dev, dtype=th.float32)
-            _lib.call("rgm_scg_select", _lib.ptr(total), _lib.ptr(seg_cand), _lib.ptr(seg_out), _lib.ptr(idx), N, B,
-                      seg_out[0].numel(), stream)
-            if self._trace is not None:
-                self._trace.append((total.view(N, B).clone(), idx.clone()))
-            subs.append(seg_out)
+            like = mean_c[:, :, start // 8: end // 8]
+            subs.append(self._select(total, seg_cand, Nl, B, like, n0, shard, False, t, None))
         return th.concat(subs, dim=-2)
+
+    def _select(self, total, cand, Nl, B, like, n0, shard, record, t, each):
+        """First-max argmax over the candidates and gather of the winners (reference :539-554): the device kernel over
+        this rank's Nl candidates, then -- when the candidates are sharded -- the exchange across ranks.
+        `like` gives the shape of one winner per sample ([B, C, h, W])."""
+        dev = like.device
+        elems = like[0].numel()
+        idx = th.zeros(B, device=dev, dtype=th.int64)
+        sample = th.zeros(B, *like.shape[1:], device=dev, dtype=th.float32)
+        if Nl > 0:
+            _lib.call("rgm_scg_select", _lib.ptr(total), _lib.ptr(cand), _lib.ptr(sample), _lib.ptr(idx), Nl, B, elems,
+                      _lib.stream_ptr())
+        if shard is not None:
+            if Nl > 0:
+                best = total.view(Nl, B).gather(0, idx.view(1, B)).view(B)
+            else:
+                best = th.full((B,), float("-inf"), device=dev)
+            sample, gidx = dist_util.first_max_over_ranks(best, idx + n0, sample, group=shard[2])
+        else:
+            gidx = idx
+        if self._trace is not None:
+            self._trace.append((None if total is None else total.view(Nl, B).clone(), gidx.clone()))
+        if record and shard is None:
+            self._record(t, total, idx, each, Nl, B)
+        return sample
 
     @staticmethod
     def _rule_is_native(name):
@@ -412,6 +443,76 @@ class GaussianDiffusion:
             loss = loss_fn(gen, tgt.to(gen.device).repeat(N, 1)).view(N, B)
             self.each_loss.setdefault(name, []).append((t0, loss[idx, th.arange(B, device=loss.device)][0].item()))
 
+    # ---- whole-step CUDA graphs ------------------------------------------------------------------------------------
+    def enable_cuda_graphs(self, on=True):
+        """Capture each distinct kind of step (sampler, guidance on/off, last step, shapes, rule set) into a CUDA graph
+        the second time it occurs and replay it afterwards: one graph launch instead of ~3000 kernel launches and the
+        Python between them.  The timestep is a device tensor and every schedule coefficient is gathered on the device,
+        so one graph serves all timesteps of its kind.  Steps that call back into user Python (cond_fn, denoised_fn,
+        rules or losses the kernels do not know, record=True, the SCG trace hook) always run eagerly.  Results are
+        bit-identical to eager execution: the same kernels run in the same order and torch's Philox generator advances
+        by the same offsets."""
+        self._graphs_on = bool(on)
+        if not on:
+            self._graphs = {}
+        return self
+
+    def _graphable(self, x, kw):
+        if not x.is_cuda or kw["cond_fn"] is not None or kw["denoised_fn"] is not None or kw["record"]:
+            return False
+        if self._trace is not None:
+            return False
+        mk = kw["model_kwargs"] or {}
+        if kw["scg_kwargs"] is not None:
+            sh = dist_util.candidate_sharding()
+            if sh is not None and dist_util.dist.get_backend(sh[2]) != "nccl":
+                return False  # the gloo exchange stages through the host
+            if not all(self._rule_is_native(n) and LOSS_DICT.get(n) in NATIVE_LOSS_KIND for n in mk.get("rule", {})):
+                return False
+            em = kw["embed_model"]
+            if em is not None and not hasattr(em, "decode_latents"):
+                return False
+        return True
+
+    @staticmethod
+    def _sig(v):
+        """Hashable signature of a step argument: tensors by storage identity (a graph bakes their addresses in)."""
+        if isinstance(v, th.Tensor):
+            return ("T", v.data_ptr(), tuple(v.shape), str(v.dtype))
+        if isinstance(v, dict):
+            return tuple((k, GaussianDiffusion._sig(x)) for k, x in v.items())
+        if isinstance(v, (int, float, str, bool)) or v is None:
+            return v
+        return ("O", id(v))  # models, decoders: by identity
+
+    def _graphed_step(self, name, eager, model, x, t, t0, kw):
+        # of guidance_kwargs a step reads the on/off decision (host-side, from t0) and the per-segment base length
+        g = kw["guidance_kwargs"]
+        dc_base = getattr(getattr(g, "dc", None), "base", 0)
+        sh = dist_util.candidate_sharding()
+        key = (name, self._sig(model), tuple(x.shape), str(x.device), self._use_guidance(t0, g), dc_base,
+               None if sh is None else sh[:2],
+               t0 > self.t_end, self.t_end, tuple((k, self._sig(v)) for k, v in kw.items() if k != "guidance_kwargs"))
+        ent = self._graphs.get(key)
+        if ent is None:
+            # first occurrence: eager (also grows the library's workspaces, which a capture must not do)
+            self._graphs[key] = False
+            return eager(model, x, t, t0, **kw)
+        if ent is False:
+            ent = _StepGraph()
+            ent.x = x.clone()
+            ent.t = t.clone()
+            th.cuda.synchronize(x.device)
+            ent.graph = th.cuda.CUDAGraph()
+            with th.cuda.graph(ent.graph):
+                ent.out = eager(model, ent.x, ent.t, t0, **kw)
+            ent.launches = None
+            self._graphs[key] = ent
+        ent.x.copy_(x)
+        ent.t.copy_(t)
+        ent.graph.replay()
+        return {k: v.clone() for k, v in ent.out.items()}
+
     # ---- one ancestral step (reference :635-735) -----------------------------------------------------------------
     @staticmethod
     def _use_guidance(t0, guidance_kwargs):
@@ -425,6 +526,16 @@ class GaussianDiffusion:
                  embed_model=None, scale_factor=1., guidance_kwargs=None, scg_kwargs=None, edit_kwargs=None,
                  record=False, _t_host=None):
         t0 = int(t[0]) if _t_host is None else _t_host  # the loops pass the index they built t from: no sync
+        kw = dict(clip_denoised=clip_denoised, denoised_fn=denoised_fn, cond_fn=cond_fn, model_kwargs=model_kwargs,
+                  embed_model=embed_model, scale_factor=scale_factor, guidance_kwargs=guidance_kwargs,
+                  scg_kwargs=scg_kwargs, edit_kwargs=edit_kwargs, record=record)
+        if self._graphs_on and self._graphable(x, kw):
+            return self._graphed_step("p_sample", self._p_sample_eager, model, x, t, t0, kw)
+        return self._p_sample_eager(model, x, t, t0, **kw)
+
+    def _p_sample_eager(self, model, x, t, t0, clip_denoised=True, denoised_fn=None, cond_fn=None, model_kwargs=None,
+                        embed_model=None, scale_factor=1., guidance_kwargs=None, scg_kwargs=None, edit_kwargs=None,
+                        record=False):
         use_guidance = self._use_guidance(t0, guidance_kwargs)
         out = self.p_mean_variance(model, x, t, clip_denoised=clip_denoised, denoised_fn=denoised_fn,
                                    model_kwargs=model_kwargs, cond_fn=cond_fn, embed_model=embed_model,
@@ -454,6 +565,16 @@ class GaussianDiffusion:
                     embed_model=None, scale_factor=1., guidance_kwargs=None, scg_kwargs=None, edit_kwargs=None,
                     record=False, _t_host=None):
         t0 = int(t[0]) if _t_host is None else _t_host
+        kw = dict(clip_denoised=clip_denoised, denoised_fn=denoised_fn, cond_fn=cond_fn, model_kwargs=model_kwargs,
+                  eta=eta, embed_model=embed_model, scale_factor=scale_factor, guidance_kwargs=guidance_kwargs,
+                  scg_kwargs=scg_kwargs, edit_kwargs=edit_kwargs, record=record)
+        if self._graphs_on and self._graphable(x, kw):
+            return self._graphed_step("ddim_sample", self._ddim_sample_eager, model, x, t, t0, kw)
+        return self._ddim_sample_eager(model, x, t, t0, **kw)
+
+    def _ddim_sample_eager(self, model, x, t, t0, clip_denoised=True, denoised_fn=None, cond_fn=None,
+                           model_kwargs=None, eta=0.0, embed_model=None, scale_factor=1., guidance_kwargs=None,
+                           scg_kwargs=None, edit_kwargs=None, record=False):
         use_guidance = self._use_guidance(t0, guidance_kwargs)
         out = self.p_mean_variance(model, x, t, clip_denoised=clip_denoised, denoised_fn=denoised_fn,
                                    model_kwargs=model_kwargs, cond_fn=cond_fn, embed_model=embed_model,

@@ -67,19 +67,24 @@ class SpacedDiffusion(GaussianDiffusion):
     def _wrap_model(self, model):
         if isinstance(model, _WrappedModel):
             return model
-        return _WrappedModel(model, self.timestep_map, self.rescale_timesteps, self.original_num_steps)
+        # the device copies of timestep_map are shared by every wrapper this diffusion hands out: a wrapper is built
+        # per call, and a fresh host->device copy per step would be a pageable transfer (illegal in a graph capture)
+        if not hasattr(self, "_dev_maps"):
+            self._dev_maps = {}
+        return _WrappedModel(model, self.timestep_map, self.rescale_timesteps, self.original_num_steps,
+                             maps=self._dev_maps)
 
     def _scale_timesteps(self, t):
         return t  # scaling is done by the wrapped model (respace.py:111-113)
 
 
 class _WrappedModel:
-    def __init__(self, model, timestep_map, rescale_timesteps, original_num_steps):
+    def __init__(self, model, timestep_map, rescale_timesteps, original_num_steps, maps=None):
         self.model = model
         self.timestep_map = timestep_map
         self.rescale_timesteps = rescale_timesteps
         self.original_num_steps = original_num_steps
-        self._maps = {}
+        self._maps = {} if maps is None else maps
 
     def __call__(self, x, ts, **kwargs):
         key = (str(ts.device), ts.dtype)

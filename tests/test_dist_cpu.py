@@ -68,3 +68,76 @@ def test_two_rank_gloo():
     assert torch.equal(res[0][5], res[1][5])                                    # same gathered tensor everywhere
     assert torch.equal(res[0][5][:4], res[0][4]) and torch.equal(res[0][5][4:7], res[1][4])  # rank order
     assert res[0][6] == res[1][6] == 11.0                                       # slowest rank's time
+
+
+# ---- candidate-sharded SCG: the per-step exchange ---------------------------------------------------------------------
+def _scores(N, B):
+    """Injected candidate scores with ties inside a shard, across shards, and a sample whose maximum sits in the last
+    shard."""
+    g = torch.Generator().manual_seed(5)
+    s = torch.randn(N, B, generator=g)
+    if N >= 8:
+        s[1, 0] = s[4, 0] = s[6, 0] = 9.0  # three-way tie across shards: index 1 must win
+        s[2, 1] = s[3, 1] = 8.0            # tie inside a shard
+    s[N - 1, 2] = 7.0                      # winner in the last shard
+    s[:, 3] = 0.5                          # all equal: index 0
+    return s
+
+
+def _exchange_worker(rank, world, port, q, N, B):
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1",
+                      MASTER_PORT=str(port))
+    from rule_guided_music_b200.guided_diffusion import dist_util
+
+    dist_util.setup_dist("cpu")
+    assert dist_util.shard_candidates(True)
+    r, w, group = dist_util.candidate_sharding()
+    s = _scores(N, B)
+    g = torch.Generator().manual_seed(6)
+    cand = torch.randn(N, B, 4, 8, 16, generator=g)      # every rank can build all candidates; it only uses its rows
+    n0, n1 = dist_util.shard_range(N, r, w)
+    if n1 > n0:
+        loc = s[n0:n1]
+        top = loc.max(0).values
+        li = ((loc == top).cumsum(0) == 0).sum(0)            # first maximal local index
+        best = loc[li, torch.arange(B)]
+        win = cand[n0:n1][li, torch.arange(B)]
+    else:
+        li = torch.zeros(B, dtype=torch.long)
+        best = torch.full((B,), float("-inf"))
+        win = torch.zeros(B, 4, 8, 16)
+    out, gidx = dist_util.first_max_over_ranks(best, li + n0, win, group=group)
+    dist_util.barrier()
+    q.put((rank, out.numpy().copy(), gidx.numpy().copy()))
+
+
+def _run_exchange(world, N, B=4):
+    port = _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_exchange_worker, args=(r, world, port, q, N, B)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=60) for _ in range(world)], key=lambda r: r[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    s = _scores(N, B)
+    g = torch.Generator().manual_seed(6)
+    cand = torch.randn(N, B, 4, 8, 16, generator=g)
+    want_idx = torch.from_numpy(s.numpy().argmax(axis=0))    # numpy argmax = first maximal index, like torch on CPU
+    want = cand[want_idx, torch.arange(B)]
+    for _, out, gidx in res:
+        assert torch.equal(torch.from_numpy(gidx), want_idx)  # index work: exact
+        assert torch.equal(torch.from_numpy(out), want)       # the winner's bits, untouched
+    return want_idx
+
+
+def test_candidate_exchange_two_ranks():
+    idx = _run_exchange(2, N=8)
+    assert idx[0] == 1 and idx[1] == 2 and idx[2] == 7 and idx[3] == 0
+
+
+def test_candidate_exchange_more_ranks_than_candidates():
+    """N = 2 candidates over 3 ranks: the last rank has nothing to offer and still takes part in the exchange."""
+    _run_exchange(3, N=2)

@@ -251,6 +251,22 @@ def run_b200(args):
         tensor_peak = peaks.get("bf16_tflops_sustained", 1400.0)
         peak_src = "measured (MEASURED_PEAKS.json bf16_tflops_sustained)" if peaks else "fallback (B200_PROFILING.md)"
         gemm = {n: v for n, v in prof.items() if n.startswith("gemm_tc")}
+        # the launch shape that takes the largest share of the step, with its DRAM traffic from the committed ncu capture
+        dominant, traffic = None, None
+        if gemm:
+            dn, dv = max(gemm.items(), key=lambda kv: kv[1]["ms"])
+            d_ach = dv["flops_alg"] / (dv["ms"] * 1e-3) / 1e12 if dv["ms"] > 0 else 0.0
+            dominant = {"launch": dn, "launches_per_step": dv["launches"] / max(args.prof_steps, 1),
+                        "avg_launch_ms": dv["ms"] / max(dv["launches"], 1), "achieved": d_ach,
+                        "frac": d_ach / tensor_peak, "algorithmic_flops_per_launch": dv["flops_alg"] / max(dv["launches"], 1)}
+            try:
+                tr = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json"))).get(dn)
+                if tr and B == B_FULL and N == N_FULL:
+                    traffic = tr["traffic_bytes"]
+                    dominant.update(algorithmic_bytes_per_launch=tr["algorithmic_bytes"], traffic_bytes_per_launch=traffic,
+                                    traffic_source="profiles/r1_vae_convs.ncu.txt / r1_dit_linears.ncu.txt (ncu --set full)")
+            except Exception:
+                pass
         g_ms = sum(v["ms"] for v in gemm.values())
         g_alg = sum(v["flops_alg"] for v in gemm.values())
         g_exec = sum(v["flops_exec"] for v in gemm.values())
@@ -275,7 +291,7 @@ def run_b200(args):
             "launch_mode": ("cuda graph replay, %d kernel nodes per step" % launches_per_step) if graphed else "eager",
             "clocks": clk,
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": tensor_peak, "unit": "TFLOP/s",
-                         "frac": achieved / tensor_peak, "traffic": None,
+                         "frac": achieved / tensor_peak, "traffic": traffic, "dominant_launch": dominant,
                          "kernel": "gemm_tc_kernel (tcgen05 implicit GEMM: every DiT linear and VAE convolution)",
                          "peak_source": peak_src, "launches_per_step": g_n / max(args.prof_steps, 1),
                          "executed_tflops": g_exec / (g_ms * 1e-3) / 1e12 if g_ms > 0 else 0.0,

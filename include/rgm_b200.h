@@ -69,6 +69,11 @@ int rgm_vae_set_lanes(rgm_vae* h, int lanes);
 /* AutoencoderKL.init_from_ckpt (klvae_pedal.py:50-59), one tensor per call; keys "post_quant_conv.*", "decoder.*".
  * Same return convention as rgm_dit_load. */
 int rgm_vae_load(rgm_vae* h, const char* key, const float* src, long long numel, void* stream);
+/* AutoencoderKL.encode_save(x, range_fix=False) (klvae_pedal.py:60-68): Encoder (model.py:342-433) + quant_conv.
+ * x f32 NCHW [n, 3, 128, 128] (piano-roll tiles in [-1, 1]) -> moments f32 NCHW [n, 2*z_channels, 16, 16]
+ * (mean | log-variance).  Weights: the checkpoint's encoder.* and quant_conv.* keys through rgm_vae_load. */
+int rgm_vae_encode(rgm_vae* h, const float* x, float* moments, int n, void* stream);
+
 /* _decode(pred_zstart, embed_model, scale_factor) (guided_diffusion/gaussian_diffusion.py:1347-1358):
  * lat f32 [n_cand, 4, Hlat, 16] -> roll f32 [n_cand, roll_ch, 128, 8*Hlat], roll_ch in [1, out_ch] (the rules read
  * channel 0 only, music_rules.py:31,56).  embed_model.decode(z [n,4,16,16]) is the case Hlat = 16, scale_factor = 1
@@ -107,12 +112,13 @@ int rgm_scg_select(const float* total, const float* cand, float* out, long long*
 int rgm_gemm_f16(const void* a16, const void* b16, const float* bias, float* out32, int M, int N, int K, int block_n,
                  void* stream);
 /* NHWC fp16 convolution with fp32 accumulation           (torch.nn.Conv2d; reference model.py:38-53,78-137)
- * kind: 0 = 1x1, 1 = 3x3 pad 1, 2 = nearest-2x upsample + 3x3 pad 1 (weights packed by rgm_pack_conv_weight)
+ * kind: 0 = 1x1, 1 = 3x3 pad 1, 2 = nearest-2x upsample + 3x3 pad 1, 3 = Downsample: pad (0,1,0,1) + 3x3 stride 2
+ * (reference model.py:55-75)  (weights packed by rgm_pack_conv_weight)
  * x16 [n,H,W,Cin], out16 [n,H',W',Cout], optional resid16 like out16; gn_part may be NULL */
 int rgm_conv_f16(const void* x16, const void* w16_packed, const float* bias, const void* resid16, void* out16,
                  int n_img, int H, int W, int Cin, int Cout, int kind, int block_n, float* gn_part, void* stream);
 /* weight fp32 [Cout,Cin,kh,kw] (torch layout) -> packed fp16 rows for rgm_conv_f16; cin_pad >= Cin (multiple of 64),
- * cout_pad >= Cout. Output size: kind 0: cout_pad*cin_pad; kind 1: cout_pad*9*cin_pad; kind 2: 4*cout_pad*4*cin_pad */
+ * cout_pad >= Cout. Output size: kind 0: cout_pad*cin_pad; kind 1, 3: cout_pad*9*cin_pad; kind 2: 4*cout_pad*4*cin_pad */
 int rgm_pack_conv_weight(const float* w32, void* w16_packed, int Cout, int Cin, int cout_pad, int cin_pad, int kind,
                          void* stream);
 /* softmax(q k^T * scale) v per (sample, head) (dit.py:274-277): q,k fp16 [B,heads,T,dh], vt fp16 [B,heads,dh,T],

@@ -1,8 +1,11 @@
-"""taming KL-VAE decoder (post_quant_conv + Decoder), torch fp32 on CPU, functional over a reference-keyed state dict.
+"""taming KL-VAE decoder (post_quant_conv + Decoder) and encoder (Encoder + quant_conv), torch fp32 on CPU, functional
+over a reference-keyed state dict.
 
 Follows taming/models/klvae_pedal.py:80-85 and taming/modules/diffusionmodules/model.py: nonlinearity :29-31,
 Normalize :34-35 (GroupNorm 32 groups, eps 1e-6), Upsample :49-53, ResnetBlock :117-137, AttnBlock :168-192,
 Decoder.forward :506-537; and the latent re-tiling of gaussian_diffusion.py:1347-1358 (_decode).
+Encoder side: Downsample :55-75 (pad right/bottom by one, 3x3 stride 2), Encoder.forward :403-433,
+AutoencoderKL.encode_save klvae_pedal.py:60-68, and the roll re-tiling of gaussian_diffusion.py:1382-1395 (_encode).
 """
 import torch
 import torch.nn.functional as F
@@ -72,3 +75,31 @@ def decode_latents(sd, pred_zstart, scale_factor=1.0, threshold=False):
     if threshold:
         roll[roll <= -0.95] = -1.0
     return roll
+
+
+def vae_encode(sd, x, num_levels=4, num_res_blocks=2):
+    """x [n,3,128,128] -> moments [n,8,16,16]   (AutoencoderKL.encode_save, range_fix=False)."""
+    h = _conv(sd, "encoder.conv_in", x, 1)
+    for lvl in range(num_levels):
+        for b in range(num_res_blocks):
+            h = _res(sd, f"encoder.down.{lvl}.block.{b}", h)
+        if lvl != num_levels - 1:
+            p = f"encoder.down.{lvl}.downsample.conv"
+            h = F.conv2d(F.pad(h, (0, 1, 0, 1), mode="constant", value=0), sd[p + ".weight"], sd[p + ".bias"], stride=2)
+    h = _res(sd, "encoder.mid.block_1", h)
+    h = _attn(sd, "encoder.mid.attn_1", h)
+    h = _res(sd, "encoder.mid.block_2", h)
+    h = _swish(_gn(sd, "encoder.norm_out", h))
+    h = _conv(sd, "encoder.conv_out", h, 1)
+    return _conv(sd, "quant_conv", h, 0)
+
+
+def encode_rolls(sd, roll, scale_factor=1.0):
+    """gaussian_diffusion.py:1382-1395: piano roll [B,3,128,L] -> latent [B,4,L/8,16] (posterior mean * scale)."""
+    H, W = roll.shape[-2], roll.shape[-1]
+    seq = W // H
+    micro = torch.cat(torch.chunk(roll, seq, dim=-1), dim=0)
+    micro = vae_encode(sd, micro)
+    z = torch.chunk(micro, 2, dim=1)[0] if micro.shape[1] == 8 else micro
+    z = torch.cat(torch.chunk(z, seq, dim=0), dim=-1)
+    return z.permute(0, 1, 3, 2) * scale_factor

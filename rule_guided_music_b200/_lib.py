@@ -48,6 +48,7 @@ _SIGNATURES = {
     "rgm_vae_destroy": [c_void_p],
     "rgm_vae_set_lanes": [c_void_p, c_int],
     "rgm_vae_load": [c_void_p, c_char_p, c_void_p, c_ll, c_void_p],
+    "rgm_vae_encode": [c_void_p, c_void_p, c_void_p, c_int, c_void_p],
     "rgm_vae_decode_latents": [c_void_p, c_void_p, c_float, c_void_p, c_int, c_int, c_int, c_void_p],
     "rgm_rule_pitch_hist": [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p],
     "rgm_rule_note_density": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p],

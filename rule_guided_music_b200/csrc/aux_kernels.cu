@@ -231,6 +231,83 @@ cudaError_t launch_vae_stem(const float* lat, float scale, const float* pq_w, co
   return done();
 }
 
+// Encoder.conv_in: one block = 16x16 output pixels of one image; the 18x18xCin fp32 halo and all weights sit in
+// shared memory, a thread owns one pixel and walks the output channels (8 at a time -> one 16-byte store).
+__global__ void __launch_bounds__(256) vae_enc_stem_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                           const float* __restrict__ b, __half* __restrict__ out,
+                                                           int Cin, int Cout) {
+  extern __shared__ float sm[];
+  float* halo = sm;                        // [Cin][18][18]
+  float* wsm = sm + Cin * 324;             // [Cout][Cin*9]
+  float* bsm = wsm + Cout * Cin * 9;       // [Cout]
+  const int img = blockIdx.z, by = blockIdx.y * 16, bx = blockIdx.x * 16;
+  const int K = Cin * 9;
+  for (int i = threadIdx.x; i < Cin * 324; i += blockDim.x) {
+    const int c = i / 324, r = (i % 324) / 18, q = i % 18;
+    const int yy = by + r - 1, xx = bx + q - 1;
+    halo[i] = (yy >= 0 && yy < 128 && xx >= 0 && xx < 128) ? x[(((long long)img * Cin + c) * 128 + yy) * 128 + xx] : 0.f;
+  }
+  for (int i = threadIdx.x; i < Cout * K; i += blockDim.x) wsm[i] = w[i];  // torch layout [Cout][Cin][3][3]
+  for (int i = threadIdx.x; i < Cout; i += blockDim.x) bsm[i] = b[i];
+  __syncthreads();
+  const int r = threadIdx.x >> 4, q = threadIdx.x & 15;
+  float in[36];
+  for (int c = 0; c < Cin; ++c)
+#pragma unroll
+    for (int t = 0; t < 9; ++t) in[c * 9 + t] = halo[c * 324 + (r + t / 3) * 18 + q + t % 3];
+  __half* orow = out + (((long long)img * 128 + by + r) * 128 + bx + q) * Cout;
+  for (int co = 0; co < Cout; co += 8) {
+    uint4 pk;
+    __half2* h2 = reinterpret_cast<__half2*>(&pk);
+#pragma unroll
+    for (int u = 0; u < 8; u += 2) {
+      float a0 = bsm[co + u], a1 = bsm[co + u + 1];
+      for (int k = 0; k < K; ++k) {
+        a0 = fmaf(wsm[(co + u) * K + k], in[k], a0);
+        a1 = fmaf(wsm[(co + u + 1) * K + k], in[k], a1);
+      }
+      h2[u >> 1] = __floats2half2_rn(a0, a1);
+    }
+    *reinterpret_cast<uint4*>(orow + co) = pk;
+  }
+}
+
+cudaError_t launch_vae_enc_stem(const float* x, const float* w, const float* b, __half* out, int n, int Cin, int Cout,
+                                cudaStream_t s) {
+  if (Cin < 1 || Cin > 4 || Cout % 8 != 0 || n <= 0) return cudaErrorInvalidValue;
+  const size_t smem = (size_t)(Cin * 324 + Cout * Cin * 9 + Cout) * sizeof(float);
+  if (smem > 48 * 1024) return cudaErrorInvalidValue;
+  ProfScope prof("vae_enc_stem", 0, 0, (double)n * 16384.0 * (Cout * 2.0 + Cin * 4.0), s);
+  vae_enc_stem_kernel<<<dim3(8, 8, n), 256, smem, s>>>(x, w, b, out, Cin, Cout);
+  return done();
+}
+
+// quant_conv: thread per (image, pixel); C <= 8 channels in, C out, fp32; output NCHW
+__global__ void __launch_bounds__(256) vae_quant_kernel(const float* __restrict__ h, int ld, const float* __restrict__ w,
+                                                        const float* __restrict__ b, float* __restrict__ moments,
+                                                        long long total, int HW, int C) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const long long img = i / HW;
+  const int pix = (int)(i - img * HW);
+  float v[8];
+  for (int c = 0; c < C; ++c) v[c] = h[i * ld + c];
+  for (int o = 0; o < C; ++o) {
+    float a = b[o];
+    for (int c = 0; c < C; ++c) a = fmaf(w[o * C + c], v[c], a);
+    moments[(img * C + o) * HW + pix] = a;
+  }
+}
+
+cudaError_t launch_vae_quant(const float* h, int ld, const float* w, const float* b, float* moments, int n, int HW,
+                             int C, cudaStream_t s) {
+  if (C < 1 || C > 8 || ld < C) return cudaErrorInvalidValue;
+  const long long total = (long long)n * HW;
+  ProfScope prof("vae_quant", 0, 0, (double)total * (ld + C) * 4.0, s);
+  vae_quant_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(h, ld, w, b, moments, total, HW, C);
+  return done();
+}
+
 // GroupNorm statistics straight from the tensor: one block per (image, 8-channel slab); used where no conv epilogue
 // produced partial sums (the stem output).  Accumulates in fp32 per thread, double across the block.
 __global__ void __launch_bounds__(256) gn_stats_kernel(const __half* __restrict__ x, const float* __restrict__ gamma,
@@ -371,8 +448,13 @@ __global__ void __launch_bounds__(256, 6) gn_apply_kernel(const __half* __restri
       const float2 f = __half22float2(h2[j]);
       float v0 = fmaf(a[2 * j], f.x, b[2 * j]), v1 = fmaf(a[2 * j + 1], f.y, b[2 * j + 1]);
       if (SWISH) {
-        v0 = __fdividef(v0, 1.0f + __expf(-v0));
-        v1 = __fdividef(v1, 1.0f + __expf(-v1));
+        // two sigmoids from ONE reciprocal: 1/d0 = d1 * rcp(d0 d1).  The kernel sits at the MUFU limit (2 per element
+        // would be 116 ms of a step against 122 ms of HBM time); this makes it 1.5.  If d0 d1 overflows, rcp gives 0
+        // and both outputs are 0: the true values are then below fp16's smallest subnormal anyway.
+        const float d0 = 1.0f + __expf(-v0), d1 = 1.0f + __expf(-v1);
+        const float r = __frcp_rn(d0 * d1);
+        v0 *= r * d1;
+        v1 *= r * d0;
       }
       o2[j] = __floats2half2_rn(v0, v1);
     }
@@ -497,8 +579,10 @@ __global__ void __launch_bounds__(512) vae_out_kernel(const __half* __restrict__
         for (int j = 0; j < 4; ++j) {
           const float2 f = __half22float2(h2[j]);
           float v0 = fmaf(ga[2 * j], f.x, gb[2 * j]), v1 = fmaf(ga[2 * j + 1], f.y, gb[2 * j + 1]);
-          v0 = __fdividef(v0, 1.0f + __expf(-v0));
-          v1 = __fdividef(v1, 1.0f + __expf(-v1));
+          const float d0 = 1.0f + __expf(-v0), d1 = 1.0f + __expf(-v1);  // one reciprocal for two sigmoids, as in
+          const float r = __frcp_rn(d0 * d1);                             // gn_apply_kernel
+          v0 *= r * d1;
+          v1 *= r * d0;
           o2[j] = __floats2half2_rn(v0, v1);  // the same fp16 rounding the stand-alone GroupNorm pass applies
         }
       }

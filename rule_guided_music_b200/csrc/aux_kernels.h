@@ -50,6 +50,14 @@ cudaError_t launch_gn_apply(const __half* x, const float2* ab, __half* y, int n,
 // x fp16 NHWC [n,128,128,C] (raw, before GroupNorm), ab its GroupNorm affine, roll f32 [n_cand, roll_ch, 128, roll_len]
 cudaError_t launch_vae_out(const __half* x, const float2* ab, const float* w, const float* bias, float* roll, int n,
                            int C, int out_ch, int tile0, int n_cand, int roll_len, int roll_ch, cudaStream_t s);
+// ---- VAE encoder (reference model.py:342-433, klvae_pedal.py:60-68) ---------------------------------------------
+// Encoder.conv_in 3x3 (model.py:355-359, 3 -> Cout channels), fp32 math: x f32 NCHW [n, Cin<=4, 128, 128] ->
+// out fp16 NHWC [n, 128, 128, Cout]
+cudaError_t launch_vae_enc_stem(const float* x, const float* w, const float* b, __half* out, int n, int Cin, int Cout,
+                                cudaStream_t s);
+// quant_conv 1x1 (klvae_pedal.py:62): h f32 NHWC [n, HW, ld] (first C channels) -> moments f32 NCHW [n, C, HW]
+cudaError_t launch_vae_quant(const float* h, int ld, const float* w, const float* b, float* moments, int n, int HW,
+                             int C, cudaStream_t s);
 // row softmax fp32 [rows, cols] -> fp16 (AttnBlock, model.py:183)
 cudaError_t launch_softmax_rows(const float* x, __half* y, long long rows, int cols, cudaStream_t s);
 // batched transpose fp16 [n, R, C] -> [n, C, R]

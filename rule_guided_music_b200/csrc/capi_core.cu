@@ -55,7 +55,7 @@ void prof_close(cudaStream_t st) {
 // weight fp32 [Cout,Cin,kh,kw] -> packed fp16 [rows][taps*cin_pad]
 __global__ void pack_conv_weight_kernel(const float* __restrict__ w, __half* __restrict__ out, int Cout, int Cin,
                                         int cout_pad, int cin_pad, int kind) {
-  const int taps = kind == 0 ? 1 : (kind == 1 ? 9 : 4);
+  const int taps = kind == 0 ? 1 : ((kind == 1 || kind == 3) ? 9 : 4);  // 3 = stride-2 Downsample conv: plain 9 taps
   const int npar = kind == 2 ? 4 : 1;
   const long long K = (long long)taps * cin_pad;
   const long long total = (long long)npar * cout_pad * K;
@@ -69,7 +69,7 @@ __global__ void pack_conv_weight_kernel(const float* __restrict__ w, __half* __r
     if (co < Cout && ci < Cin) {
       if (kind == 0) {
         v = w[(long long)co * Cin + ci];
-      } else if (kind == 1) {
+      } else if (kind == 1 || kind == 3) {
         v = w[((long long)co * Cin + ci) * 9 + t];
       } else {
         // nearest-2x upsample then 3x3: output pixel (2i+ph, 2j+pw) reads low-res rows {i+ph-1, i+ph}; tap a = 0/1.
@@ -236,7 +236,7 @@ int rgm_conv_f16(const void* x16, const void* w16_packed, const float* bias, con
 int rgm_pack_conv_weight(const float* w32, void* w16_packed, int Cout, int Cin, int cout_pad, int cin_pad, int kind,
                          void* stream) {
   if (rgm_check_device()) return -1;
-  if (kind < 0 || kind > 2 || cin_pad < Cin || cout_pad < Cout) return set_error("rgm_pack_conv_weight: bad arguments");
+  if (kind < 0 || kind > 3 || cin_pad < Cin || cout_pad < Cout) return set_error("rgm_pack_conv_weight: bad arguments");
   return check_cuda(launch_pack_conv_weight(w32, static_cast<__half*>(w16_packed), Cout, Cin, cout_pad, cin_pad, kind,
                                             static_cast<cudaStream_t>(stream)),
                     "rgm_pack_conv_weight");

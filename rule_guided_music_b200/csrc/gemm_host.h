@@ -13,6 +13,8 @@ enum ConvKind : int {
   CONV_1x1 = 0,   // also: plain linear layer
   CONV_3x3 = 1,   // 9 taps, zero padding 1
   CONV_UP2 = 2,   // nearest-2x upsample followed by 3x3 conv, run as 4 output-parity 2x2 sub-convs
+  CONV_DOWN2 = 3, // Downsample (model.py:55-75): pad right/bottom by one, 3x3 conv with stride 2; H, W are the INPUT
+                  // dims (even), the output is H/2 x W/2; loaded by TMA boxes with element strides (1, 2, 2, 1)
 };
 
 struct GemmDesc {

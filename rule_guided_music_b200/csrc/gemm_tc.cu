@@ -35,6 +35,7 @@ struct MapKey {
   unsigned long long d[4];
   unsigned long long s[3];
   unsigned box[4];
+  unsigned estr[4];
   int rank;
   bool operator==(const MapKey& o) const { return std::memcmp(this, &o, sizeof(MapKey)) == 0; }
 };
@@ -53,7 +54,7 @@ std::unordered_map<MapKey, CUtensorMap, MapKeyHash> g_maps;
 // fp16 tensor map, 128-byte swizzle, zero fill out of bounds. dims/strides innermost first; strides in bytes
 // for dims 1..rank-1.
 bool make_map(CUtensorMap* out, const void* ptr, int rank, const cuuint64_t* dims, const cuuint64_t* strides,
-              const cuuint32_t* box, std::string* err) {
+              const cuuint32_t* box, std::string* err, const cuuint32_t* elem_strides = nullptr) {
   MapKey key;
   std::memset(&key, 0, sizeof(key));
   key.ptr = ptr;
@@ -61,6 +62,7 @@ bool make_map(CUtensorMap* out, const void* ptr, int rank, const cuuint64_t* dim
   for (int i = 0; i < rank; ++i) {
     key.d[i] = dims[i];
     key.box[i] = box[i];
+    key.estr[i] = elem_strides ? elem_strides[i] : 1;
     if (i) key.s[i - 1] = strides[i - 1];
   }
   {
@@ -77,6 +79,8 @@ bool make_map(CUtensorMap* out, const void* ptr, int rank, const cuuint64_t* dim
     return false;
   }
   cuuint32_t estr[4] = {1, 1, 1, 1};
+  if (elem_strides)
+    for (int i = 0; i < rank; ++i) estr[i] = elem_strides[i];
   CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, rank, const_cast<void*>(ptr), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -186,20 +190,26 @@ cudaError_t launch_gemm(const GemmDesc& d, cudaStream_t stream, std::string* err
   // the row-major kernel with 32-column tiles serves the tiny outputs (final layer, conv_out) and odd widths
   const bool sw = col_epi && d.N % SW_FEATS == 0 && d.block_n != 32;
   const int rows_per_tile = sw ? SW_ROWS : GEMM_BLOCK_M;
+  // output grid: the input grid, except for the stride-2 Downsample conv
+  const bool down = d.conv == CONV_DOWN2;
+  if (down && (d.H % 2 != 0 || d.W % 2 != 0 || d.H < 2)) return fail("gemm: stride-2 conv needs even image dims");
+  const int oH = down ? d.H / 2 : d.H, oW = down ? d.W / 2 : d.W;
   // a linear layer (H == 1) uses boxes of rows_per_tile rows; rows past the end of A are zero-filled by TMA and
   // masked in the epilogue.  Images use full-width boxes of bh rows.
-  const int bw = (d.H == 1 || d.W >= rows_per_tile) ? rows_per_tile : d.W;
+  const int bw = (oH == 1 || oW >= rows_per_tile) ? rows_per_tile : oW;
   if (rows_per_tile % bw != 0) return fail("gemm: image width must divide the row tile");
   const int bh = rows_per_tile / bw;
-  if (bh > 1 && d.H % bh != 0) return fail("gemm: H not a multiple of the tile height");
-  if (d.H > 1 && d.W > rows_per_tile) return fail("gemm: images wider than the row tile are not supported");
-  if (d.n_img > 1 && d.H == 1 && d.W % rows_per_tile != 0)
+  if (bh > 1 && oH % bh != 0) return fail("gemm: H not a multiple of the tile height");
+  if (oH > 1 && oW > rows_per_tile) return fail("gemm: images wider than the row tile are not supported");
+  if (d.n_img > 1 && oH == 1 && oW % rows_per_tile != 0)
     return fail("gemm: batched rows must be a multiple of the row tile");
+  if (down && (2 * bw > 256 || 2 * bh > 256)) return fail("gemm: stride-2 box exceeds the TMA box limit");
   p.bw = bw;
   p.bh = bh;
-  p.tiles_per_row = (d.W + bw - 1) / bw;
-  p.tiles_per_img = p.tiles_per_row * (d.H / bh > 0 ? d.H / bh : 1);
-  p.M = d.n_img * d.H * d.W;
+  p.in_stride = down ? 2 : 1;
+  p.tiles_per_row = (oW + bw - 1) / bw;
+  p.tiles_per_img = p.tiles_per_row * (oH / bh > 0 ? oH / bh : 1);
+  p.M = d.n_img * oH * oW;
   p.N = d.N;
   p.num_m_tiles = d.n_img * p.tiles_per_img;
   p.slots_per_par = (p.M + 127) / 128;
@@ -214,6 +224,14 @@ cudaError_t launch_gemm(const GemmDesc& d, cudaStream_t stream, std::string* err
       p.tap_dy[0][t] = (signed char)(t / 3 - 1);
       p.tap_dx[0][t] = (signed char)(t % 3 - 1);
     }
+  } else if (d.conv == CONV_DOWN2) {
+    // F.pad(x, (0,1,0,1)) + conv(stride 2, padding 0): output (h, w) reads input (2h + ky, 2w + kx), ky, kx in 0..2;
+    // the padded last row / column is the TMA out-of-bounds zero fill
+    p.num_taps = 9;
+    for (int t = 0; t < 9; ++t) {
+      p.tap_dy[0][t] = (signed char)(t / 3);
+      p.tap_dx[0][t] = (signed char)(t % 3);
+    }
   } else if (d.conv == CONV_UP2) {
     p.num_taps = 4;
     p.num_par = 4;
@@ -227,6 +245,7 @@ cudaError_t launch_gemm(const GemmDesc& d, cudaStream_t stream, std::string* err
   }
   p.epi = d.e;
   p.trace = d.trace;
+  if (const char* bn = getenv("RGM_GEMM_BAND")) p.band_n = atoi(bn);  // experiment knob, read per launch
   if (const char* tp = getenv("RGM_DEBUG_TRACE_PTR")) {  // development aid: trace every launch with a given epilogue
     const char* te = getenv("RGM_DEBUG_TRACE_EPI");
     if (te && atoi(te) == d.epi && (!getenv("RGM_DEBUG_TRACE_N") || atoi(getenv("RGM_DEBUG_TRACE_N")) == d.N))
@@ -252,8 +271,11 @@ cudaError_t launch_gemm(const GemmDesc& d, cudaStream_t stream, std::string* err
     if (d.H == 1 && d.n_img == 1 && d.a_rows > d.W) wdim = (cuuint64_t)d.a_rows;
     cuuint64_t dims[4] = {(cuuint64_t)d.C, wdim, (cuuint64_t)d.H, (cuuint64_t)d.n_img};
     cuuint64_t strides[3] = {(cuuint64_t)d.lda * 2, wdim * d.lda * 2, (cuuint64_t)d.H * wdim * d.lda * 2};
-    cuuint32_t box[4] = {GEMM_BLOCK_K, (cuuint32_t)bw, (cuuint32_t)bh, 1};
-    if (!make_map(&ma, d.A, 4, dims, strides, box, err)) return cudaErrorInvalidValue;
+    // with element strides s, TMA loads ceil(box / s) elements per dimension: box = s * (elements wanted)
+    const cuuint32_t es = down ? 2 : 1;
+    cuuint32_t box[4] = {GEMM_BLOCK_K, (cuuint32_t)bw * es, (cuuint32_t)bh * es, 1};
+    cuuint32_t estr[4] = {1, es, es, 1};
+    if (!make_map(&ma, d.A, 4, dims, strides, box, err, estr)) return cudaErrorInvalidValue;
   }
   {
     const long long K = (long long)p.num_taps * d.C;
@@ -265,7 +287,8 @@ cudaError_t launch_gemm(const GemmDesc& d, cudaStream_t stream, std::string* err
 
   // CTA pairs (gemm_sw2_kernel) when there are at least two feature tiles and enough pair tiles to fill the machine
   const long long pair_tiles = (long long)p.num_m_tiles * ((p.num_n_tiles + 1) / 2) * p.num_par;
-  const bool pair = sw && pair_mode_enabled() && p.num_n_tiles >= 2 && pair_tiles >= device_sm_count() / 2;
+  const bool pair =
+      sw && !down && pair_mode_enabled() && p.num_n_tiles >= 2 && pair_tiles >= device_sm_count() / 2;
   CUtensorMap ma2;
   if (pair) {
     // this CTA's half of the 256-row activation box: half the image rows, or 128 of the 256 linear rows

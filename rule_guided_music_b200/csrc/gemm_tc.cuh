@@ -63,6 +63,8 @@ struct GemmParams {
   int tiles_per_img, tiles_per_row, bh, bw;
   int b_batched;              // B's third coordinate follows the image index (batched GEMM)
   int slots_per_par;          // GroupNorm partial slots (128-row groups) per output parity = ceil(M / 128)
+  int band_n;                 // pair kernel rasterisation: feature-tile pairs per band (0 = all: feature pairs fastest)
+  int in_stride;              // 1, or 2 for the stride-2 Downsample conv: input pixel = in_stride * output pixel + tap
   signed char tap_dy[4][9];
   signed char tap_dx[4][9];
   // development aid: when non-null, CTA 0 writes clock64() at pipeline events of each of its tiles, 8 slots per tile:
@@ -238,25 +240,29 @@ __device__ __forceinline__ void epilogue_cols_core(const GemmParams& p, const fl
     const int half_rot = e.rot_dim >> 1;
     const int b0 = row0 / e.T, tok0 = row0 - b0 * e.T;  // T is a multiple of 32: one sample per round
     __half* qp = (which == 0 ? e.q : e.k) + (((long long)b0 * e.heads + head) * e.T + tok0) * e.dh_pad + d;
-    // lanes outside the rotary dimensions read entry 0 and select (cos, sin) = (1, 0): uniform control flow, so the
-    // table loads of a whole half-round are issued back to back instead of one exposed load per row
-    const float2* tp = e.rope_cs + tok0 * half_rot + (rot ? (d >> 1) : 0);
+    // This thread's frequency is fixed for the round, so the 32 table entries it needs are one rotation apart:
+    // (cos, sin)((tok0 + j) w) = R(w)^j (cos, sin)(tok0 w).  ONE table load per round (+ the step (cos w, sin w) =
+    // the table's row of token 1) and 4 FMAs per row replace 32 loads; the table (36 KB at T = 256) does not fit the
+    // 28 KB of L1 left beside the operand ring, and those exposed L2 round trips made this epilogue 18 K cycles per
+    // tile against 12.5 K for the MMAs (profiles/r1_trace_dit.txt).  Restarting from the table every 32 rows keeps the
+    // recurrence's drift below 4e-6, under the table's own argument rounding (pos * freq in fp32).
+    // Lanes outside the rotary dimensions rotate by the identity: uniform control flow.
+    const int fi = rot ? (d >> 1) : 0;
+    const float2 cs0 = __ldg(e.rope_cs + tok0 * half_rot + fi);
+    const float2 stp = __ldg(e.rope_cs + half_rot + fi);  // token 1 (T >= 32 here)
+    float c = rot ? cs0.x : 1.f, sn = rot ? cs0.y : 0.f;
+    const float dc = rot ? stp.x : 1.f, ds = rot ? stp.y : 0.f;
     const float sgn = (d & 1) ? 1.f : -1.f;
     const int nrows = p.M - row0 < 32 ? p.M - row0 : 32;
 #pragma unroll
-    for (int hh = 0; hh < 2; ++hh) {
-      float2 cs[16];
-#pragma unroll
-      for (int j = 0; j < 16; ++j) cs[j] = __ldg(tp + (hh * 16 + j) * half_rot);
-#pragma unroll
-      for (int jj = 0; jj < 16; ++jj) {
-        const int j = hh * 16 + jj;
-        const float x = val[j] + bias;
-        const float px = __shfl_xor_sync(0xffffffffu, x, 1);
-        const float c = rot ? cs[jj].x : 1.f, sn = rot ? cs[jj].y : 0.f;
-        const float y = fmaf(px * sgn, sn, x * c);
-        if (j < nrows) qp[(long long)j * e.dh_pad] = __float2half_rn(y);
-      }
+    for (int j = 0; j < 32; ++j) {
+      const float x = val[j] + bias;
+      const float px = __shfl_xor_sync(0xffffffffu, x, 1);
+      const float y = fmaf(px * sgn, sn, x * c);
+      if (j < nrows) qp[(long long)j * e.dh_pad] = __float2half_rn(y);
+      const float c2 = fmaf(c, dc, -sn * ds);
+      sn = fmaf(sn, dc, c * ds);
+      c = c2;
     }
   }
 }
@@ -409,8 +415,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           const int m_tile = ms * MT + mt;  // may be == num_m_tiles for the odd tail: image index out of range -> zeros
           img[mt] = m_tile / p.tiles_per_img;
           const int rr = m_tile - img[mt] * p.tiles_per_img;
-          h0[mt] = (rr / p.tiles_per_row) * p.bh;
-          w0[mt] = (rr % p.tiles_per_row) * p.bw;
+          h0[mt] = (rr / p.tiles_per_row) * p.bh * p.in_stride;
+          w0[mt] = (rr % p.tiles_per_row) * p.bw * p.in_stride;
         }
         const int bz = p.b_batched ? img[0] : 0;
         if (p.trace && blockIdx.x == 0) p.trace[(t / gridDim.x) * 8 + 0] = clock64();
@@ -704,8 +710,8 @@ gemm_sw_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
         const int n_tile = tt - m_tile * p.num_n_tiles;
         const int img = m_tile / p.tiles_per_img;
         const int rr = m_tile - img * p.tiles_per_img;
-        const int h0 = (rr / p.tiles_per_row) * p.bh;
-        const int w0 = (rr % p.tiles_per_row) * p.bw;
+        const int h0 = (rr / p.tiles_per_row) * p.bh * p.in_stride;
+        const int w0 = (rr % p.tiles_per_row) * p.bw * p.in_stride;
         const int wrow = par * p.N + n_tile * SW_FEATS;
         const int bz = p.b_batched ? img : 0;
         if (p.trace && blockIdx.x == 0) p.trace[(t / gridDim.x) * 8 + 0] = clock64();
@@ -806,6 +812,31 @@ constexpr uint32_t SW2_W_BYTES = SW_FEATS * GEMM_BLOCK_K * 2;       // 16 KB: th
 constexpr uint32_t SW2_X_BYTES = (SW_ROWS / 2) * GEMM_BLOCK_K * 2;  // 16 KB: this CTA's 128 of the 256 rows
 constexpr size_t SW2_SMEM_BYTES = 1024 + SW2_STAGES * (SW2_W_BYTES + SW2_X_BYTES) + 256;
 
+// Tile order of the pair kernel.  Pairs that run at the same time work on consecutive tile indices; with feature pairs
+// fastest (band = all) the ~74 concurrent pairs share few row tiles and every feature slice, with a band of `gn`
+// feature pairs they form a (74 / gn) x gn patch: each activation tile is read by gn pairs at once and each weight slice
+// by 74 / gn.  tt -> (row tile, feature pair).
+__device__ __forceinline__ void sw2_tile_coords(int tt, int num_m, int pairs_n, int gn, int& m_tile, int& n_pair) {
+  if (gn <= 0 || gn >= pairs_n) {
+    m_tile = tt / pairs_n;
+    n_pair = tt - m_tile * pairs_n;
+    return;
+  }
+  const int full = pairs_n / gn;
+  const int band_tiles = num_m * gn;
+  if (tt < full * band_tiles) {
+    const int band = tt / band_tiles;
+    const int r = tt - band * band_tiles;
+    m_tile = r / gn;
+    n_pair = band * gn + (r - m_tile * gn);
+  } else {
+    const int r = tt - full * band_tiles;
+    const int g2 = pairs_n - full * gn;
+    m_tile = r / g2;
+    n_pair = full * gn + (r - m_tile * g2);
+  }
+}
+
 template <int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
 gemm_sw2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
@@ -862,8 +893,9 @@ gemm_sw2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
       for (int t = pair_id; t < total_tiles; t += num_pairs) {
         const int par = t / tiles_mn;
         const int tt = t - par * tiles_mn;
-        const int m_tile = tt / pairs_n;
-        const int n_tile = 2 * (tt - m_tile * pairs_n) + (int)rank;
+        int m_tile, n_pair;
+        sw2_tile_coords(tt, p.num_m_tiles, pairs_n, p.band_n, m_tile, n_pair);
+        const int n_tile = 2 * n_pair + (int)rank;
         const int img = m_tile / p.tiles_per_img;
         const int rr = m_tile - img * p.tiles_per_img;
         int h0 = (rr / p.tiles_per_row) * p.bh;
@@ -932,8 +964,9 @@ gemm_sw2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
     for (int t = pair_id; t < total_tiles; t += num_pairs) {
       const int par = t / tiles_mn;
       const int tt = t - par * tiles_mn;
-      const int m_tile = tt / pairs_n;
-      const int n_tile = 2 * (tt - m_tile * pairs_n) + (int)rank;
+      int m_tile, n_pair;
+      sw2_tile_coords(tt, p.num_m_tiles, pairs_n, p.band_n, m_tile, n_pair);
+      const int n_tile = 2 * n_pair + (int)rank;
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       if (p.trace && blockIdx.x == 0 && warp == 2 && lane == 0) p.trace[(t / num_pairs) * 8 + 4] = clock64();

@@ -7,6 +7,9 @@
 //   - conv_out scattering straight into the piano roll [cand, ch, 128, 8*Hlat]      gaussian_diffusion.py:1355
 // GroupNorm apply + swish is one fp16 -> fp16 pass (aux_kernels.cu).  The latent re-tiling of _decode
 // (gaussian_diffusion.py:1347-1358), post_quant_conv and conv_in are one fp32 kernel.
+// The ENCODER (model.py:342-433 + quant_conv, klvae_pedal.py:60-68; used once per run by scripts/edit.py through
+// gaussian_diffusion._encode :1382-1395) reuses every block: conv_in is an fp32 CUDA-core kernel (3 input channels),
+// Downsample is the stride-2 implicit GEMM (TMA element strides), conv_out + quant_conv end in fp32.
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
@@ -77,6 +80,14 @@ struct Vae {
   Norm norm_out;
   float *cout_w = nullptr, *cout_b = nullptr;  // conv_out stays fp32: it runs fused on the CUDA cores (vae_out_kernel)
   int cout_cin = 0;
+  // encoder (model.py:342-433) + quant_conv
+  int in_ch = 3;
+  float *e_cin_w = nullptr, *e_cin_b = nullptr, *q_w = nullptr, *q_b = nullptr;
+  std::vector<std::vector<Res>> down;   // [level][block]
+  std::vector<Conv> downsample;         // [level] (last level unused)
+  Res e_mid1, e_mid2;
+  Norm e_attn_norm, e_norm_out;
+  Conv e_attn_q, e_attn_k, e_attn_v, e_attn_proj, e_cout;
   std::map<std::string, std::pair<float*, long long>> f32_keys;  // key -> (dst, numel)
   std::map<std::string, Conv*> conv_keys;                        // "<name>.weight" -> conv
   std::vector<void*> allocs;
@@ -115,7 +126,7 @@ struct Vae {
     c.k = k;
     c.kind = kind;
     c.cout_pad = cout % 128 == 0 ? cout : (int)((cout + 31) / 32 * 32);
-    const int taps = kind == CONV_1x1 ? 1 : (kind == CONV_3x3 ? 9 : 4);
+    const int taps = kind == CONV_1x1 ? 1 : (kind == CONV_UP2 ? 4 : 9);
     const int npar = kind == CONV_UP2 ? 4 : 1;
     c.w = alloc<__half>((long long)npar * c.cout_pad * taps * cin);
     c.b = alloc<float>(c.cout_pad);
@@ -184,6 +195,43 @@ int vae_build(Vae* m) {
   if (!ok || !m->cout_w || !m->cout_b) return set_error("rgm_vae_create: out of memory");
   m->f32_keys["decoder.conv_out.weight"] = {m->cout_w, (long long)m->out_ch * block_in * 9};
   m->f32_keys["decoder.conv_out.bias"] = {m->cout_b, m->out_ch};
+
+  // ---- encoder ---------------------------------------------------------------------------------------------
+  const int zz = 2 * m->zc;  // double_z: mean and log-variance
+  m->e_cin_w = m->alloc<float>((long long)m->ch * m->in_ch * 9);
+  m->e_cin_b = m->alloc<float>(m->ch);
+  m->q_w = m->alloc<float>((long long)zz * zz);
+  m->q_b = m->alloc<float>(zz);
+  if (!m->e_cin_w || !m->e_cin_b || !m->q_w || !m->q_b) return set_error("rgm_vae_create: out of memory");
+  m->f32_keys["encoder.conv_in.weight"] = {m->e_cin_w, (long long)m->ch * m->in_ch * 9};
+  m->f32_keys["encoder.conv_in.bias"] = {m->e_cin_b, m->ch};
+  m->f32_keys["quant_conv.weight"] = {m->q_w, (long long)zz * zz};
+  m->f32_keys["quant_conv.bias"] = {m->q_b, zz};
+  m->down.resize(m->n_levels);
+  m->downsample.resize(m->n_levels);
+  block_in = m->ch;
+  for (int lvl = 0; ok && lvl < m->n_levels; ++lvl) {
+    const int block_out = m->ch * m->mult[lvl];
+    m->down[lvl].resize(m->nres);
+    for (int b = 0; ok && b < m->nres; ++b) {
+      ok = m->make_res(m->down[lvl][b], "encoder.down." + std::to_string(lvl) + ".block." + std::to_string(b), block_in,
+                       block_out);
+      block_in = block_out;
+    }
+    if (ok && lvl != m->n_levels - 1)
+      ok = m->make_conv(m->downsample[lvl], "encoder.down." + std::to_string(lvl) + ".downsample.conv", block_in,
+                        block_in, 3, CONV_DOWN2);
+  }
+  ok = ok && m->make_res(m->e_mid1, "encoder.mid.block_1", block_in, block_in) &&
+       m->make_norm(m->e_attn_norm, "encoder.mid.attn_1.norm", block_in) &&
+       m->make_conv(m->e_attn_q, "encoder.mid.attn_1.q", block_in, block_in, 1, CONV_1x1) &&
+       m->make_conv(m->e_attn_k, "encoder.mid.attn_1.k", block_in, block_in, 1, CONV_1x1) &&
+       m->make_conv(m->e_attn_v, "encoder.mid.attn_1.v", block_in, block_in, 1, CONV_1x1) &&
+       m->make_conv(m->e_attn_proj, "encoder.mid.attn_1.proj_out", block_in, block_in, 1, CONV_1x1) &&
+       m->make_res(m->e_mid2, "encoder.mid.block_2", block_in, block_in) &&
+       m->make_norm(m->e_norm_out, "encoder.norm_out", block_in) &&
+       m->make_conv(m->e_cout, "encoder.conv_out", block_in, zz, 3, CONV_3x3);
+  if (!ok) return set_error("rgm_vae_create: out of memory");
   return 0;
 }
 
@@ -242,9 +290,15 @@ int gn_from_part(Ctx& c, const Norm& n, int H_in, bool was_up2) {
 
 // ResnetBlock (model.py:117-137). x: input [nt,H,H,cin] whose GroupNorm partials are current; t, h: scratch; out may
 // alias neither x nor h.  Leaves the partials of `out` current.
-int run_res(Ctx& c, const Res& r, const __half* x, int H, bool x_from_up2, __half* t, __half* h, __half* out) {
+int run_res(Ctx& c, const Res& r, const __half* x, int H, bool x_from_up2, __half* t, __half* h, __half* out,
+            bool stats_from_tensor = false) {
   const int HW = H * H;
-  if (gn_from_part(c, r.n1, x_from_up2 ? H / 2 : H, x_from_up2)) return -1;
+  if (stats_from_tensor) {  // x did not come out of a GEMM epilogue (the stems): one direct statistics pass
+    RGM_CUDA_OK(launch_gn_stats(x, r.n1.gamma, r.n1.beta, static_cast<float2*>(c.L->abbuf.p), c.nt, HW, r.n1.c, 1e-6f,
+                                c.st));
+  } else if (gn_from_part(c, r.n1, x_from_up2 ? H / 2 : H, x_from_up2)) {
+    return -1;
+  }
   RGM_CUDA_OK(launch_gn_apply(x, static_cast<float2*>(c.L->abbuf.p), t, c.nt, HW, r.n1.c, 1, c.st));
   if (run_conv(c, r.c1, t, H, nullptr, h, true)) return -1;
   if (gn_from_part(c, r.n2, H, false)) return -1;
@@ -255,6 +309,74 @@ int run_res(Ctx& c, const Res& r, const __half* x, int H, bool x_from_up2, __hal
     resid = out;  // conv2 adds the shortcut it finds in `out` and overwrites it (same thread reads then writes)
   }
   return run_conv(c, r.c2, t, H, resid, out, true);
+}
+
+// AttnBlock (model.py:168-192) at 16x16: single head over the 256 positions of a tile.  x = buf[cur] (its GroupNorm
+// partials current); the result x + proj_out(attention) lands in buf[0] with its partials current.  cur must be 3.
+int run_mid_attn(Ctx& c, const Norm& norm, const Conv& cq, const Conv& ck, const Conv& cvv, const Conv& cproj,
+                 __half* const* buf, int cur, int H, int C) {
+  const int nt = c.nt;
+  cudaStream_t st = c.st;
+  Vae::Lane* L = c.L;
+  float2* ab = static_cast<float2*>(L->abbuf.p);
+  const int HW = H * H;
+  __half* x = buf[cur];
+  __half* hn = buf[0];
+  if (gn_from_part(c, norm, H, false)) return -1;
+  RGM_CUDA_OK(launch_gn_apply(x, ab, hn, nt, HW, C, 0, st));
+  // q, k, v, v^T, P carve buf[1] and buf[2] (each holds >= 4 tensors of this size: buffers are sized for 128x128x256)
+  const long long tsz = (long long)nt * HW * C;
+  __half* q = buf[1];
+  __half* k = buf[1] + tsz;
+  __half* v = buf[1] + 2 * tsz;
+  __half* vT = buf[2];
+  __half* P = buf[2] + tsz;
+  __half* ao = buf[2] + 2 * tsz;
+  if (run_conv(c, cq, hn, H, nullptr, q, false)) return -1;
+  if (run_conv(c, ck, hn, H, nullptr, k, false)) return -1;
+  if (run_conv(c, cvv, hn, H, nullptr, v, false)) return -1;
+  RGM_CUDA_OK(launch_transpose(v, vT, nt, HW, C, st));
+  float* S = static_cast<float*>(L->attn_s.p);
+  {
+    GemmDesc d;  // S[b] = q[b] k[b]^T * C^-0.5
+    d.A = q;
+    d.n_img = nt;
+    d.H = 1;
+    d.W = HW;
+    d.C = C;
+    d.lda = C;
+    d.B = k;
+    d.rows_b = HW;
+    d.b_batch = nt;
+    d.N = HW;
+    d.conv = CONV_1x1;
+    d.epi = EPI_F32;
+    d.e.out = S;
+    d.e.ldo = HW;
+    d.e.alpha = 1.0f / sqrtf((float)C);
+    RGM_VGEMM_OK(d);
+  }
+  RGM_CUDA_OK(launch_softmax_rows(S, P, (long long)nt * HW, HW, st));
+  {
+    GemmDesc d;  // ao[b] = P[b] v[b]  (B operand = v^T [C, HW])
+    d.A = P;
+    d.n_img = nt;
+    d.H = 1;
+    d.W = HW;
+    d.C = HW;
+    d.lda = HW;
+    d.B = vT;
+    d.rows_b = C;
+    d.b_batch = nt;
+    d.N = C;
+    d.conv = CONV_1x1;
+    d.epi = EPI_F16;
+    d.e.out = ao;
+    d.e.ldo = C;
+    d.e.alpha = 1.f;
+    RGM_VGEMM_OK(d);
+  }
+  return run_conv(c, cproj, ao, H, x, hn, true);  // x + proj_out(attention)
 }
 
 int decode_chunk(Vae* m, Vae::Lane* L, const float* lat, float scale, float* roll, int n_cand, int Hlat, int roll_ch,
@@ -279,68 +401,9 @@ int decode_chunk(Vae* m, Vae::Lane* L, const float* lat, float scale, float* rol
     if (run_conv(c, r.c2, buf[1], H, buf[0], buf[3], true)) return -1;
   }
   int cur = 3;  // buf[cur] holds x
-  // mid.attn_1 (model.py:168-192): single head over the 256 positions of a tile
-  {
-    const int HW = H * H;
-    __half* x = buf[cur];
-    __half* hn = buf[0];
-    if (gn_from_part(c, m->attn_norm, H, false)) return -1;
-    RGM_CUDA_OK(launch_gn_apply(x, ab, hn, nt, HW, C, 0, st));
-    // q, k, v, v^T, P carve buf[1] and buf[2] (each holds >= 4 tensors of this size: buffers are sized for 128x128x256)
-    const long long tsz = (long long)nt * HW * C;
-    __half* q = buf[1];
-    __half* k = buf[1] + tsz;
-    __half* v = buf[1] + 2 * tsz;
-    __half* vT = buf[2];
-    __half* P = buf[2] + tsz;
-    __half* ao = buf[2] + 2 * tsz;
-    if (run_conv(c, m->attn_q, hn, H, nullptr, q, false)) return -1;
-    if (run_conv(c, m->attn_k, hn, H, nullptr, k, false)) return -1;
-    if (run_conv(c, m->attn_v, hn, H, nullptr, v, false)) return -1;
-    RGM_CUDA_OK(launch_transpose(v, vT, nt, HW, C, st));
-    float* S = static_cast<float*>(L->attn_s.p);
-    {
-      GemmDesc d;  // S[b] = q[b] k[b]^T * C^-0.5
-      d.A = q;
-      d.n_img = nt;
-      d.H = 1;
-      d.W = HW;
-      d.C = C;
-      d.lda = C;
-      d.B = k;
-      d.rows_b = HW;
-      d.b_batch = nt;
-      d.N = HW;
-      d.conv = CONV_1x1;
-      d.epi = EPI_F32;
-      d.e.out = S;
-      d.e.ldo = HW;
-      d.e.alpha = 1.0f / sqrtf((float)C);
-      RGM_VGEMM_OK(d);
-    }
-    RGM_CUDA_OK(launch_softmax_rows(S, P, (long long)nt * HW, HW, st));
-    {
-      GemmDesc d;  // ao[b] = P[b] v[b]  (B operand = v^T [C, HW])
-      d.A = P;
-      d.n_img = nt;
-      d.H = 1;
-      d.W = HW;
-      d.C = HW;
-      d.lda = HW;
-      d.B = vT;
-      d.rows_b = C;
-      d.b_batch = nt;
-      d.N = C;
-      d.conv = CONV_1x1;
-      d.epi = EPI_F16;
-      d.e.out = ao;
-      d.e.ldo = C;
-      d.e.alpha = 1.f;
-      RGM_VGEMM_OK(d);
-    }
-    if (run_conv(c, m->attn_proj, ao, H, x, hn, true)) return -1;  // x + proj_out(attention)
-    cur = 0;
-  }
+  // mid.attn_1 (model.py:168-192)
+  if (run_mid_attn(c, m->attn_norm, m->attn_q, m->attn_k, m->attn_v, m->attn_proj, buf, cur, H, C)) return -1;
+  cur = 0;
   // mid.block_2
   {
     const int o = (cur + 3) & 3;
@@ -373,6 +436,87 @@ int decode_chunk(Vae* m, Vae::Lane* L, const float* lat, float scale, float* rol
   return 0;
 }
 
+
+// Encoder + quant_conv for tiles [t0, t0+nt): x f32 NCHW [n, in_ch, 128, 128] -> moments f32 NCHW [n, 2*zc, 16, 16]
+int encode_chunk(Vae* m, Vae::Lane* L, const float* x, float* moments, int t0, int nt, cudaStream_t st) {
+  Ctx c{m, L, st, nt};
+  __half* buf[4];
+  for (int i = 0; i < 4; ++i) buf[i] = static_cast<__half*>(L->act[i].p);
+  float2* ab = static_cast<float2*>(L->abbuf.p);
+  int H = 128;
+  RGM_CUDA_OK(launch_vae_enc_stem(x + (long long)t0 * m->in_ch * 128 * 128, m->e_cin_w, m->e_cin_b, buf[0], nt, m->in_ch,
+                                  m->ch, st));
+  int cur = 0;
+  bool first = true;
+  for (int lvl = 0; lvl < m->n_levels; ++lvl) {
+    for (int b = 0; b < m->nres; ++b) {
+      const int o = (cur + 3) & 3;
+      if (run_res(c, m->down[lvl][b], buf[cur], H, false, buf[(cur + 1) & 3], buf[(cur + 2) & 3], buf[o], first)) return -1;
+      cur = o;
+      first = false;
+    }
+    if (lvl != m->n_levels - 1) {
+      const int o = (cur + 1) & 3;
+      if (run_conv(c, m->downsample[lvl], buf[cur], H, nullptr, buf[o], true)) return -1;  // stride 2: H -> H/2
+      cur = o;
+      H /= 2;
+    }
+  }
+  if (H != 16) return set_error("rgm_vae_encode: encoder output is not 16x16");
+  const int C = m->e_mid1.c1.cin;
+  {
+    const int o = 3;  // run_mid_attn wants its input in buf[3]
+    if (cur == o) {   // (with 4 levels x 2 blocks + 3 downsamples cur is 3 here only by accident of the ping-pong)
+      const int o2 = (cur + 3) & 3;
+      if (run_res(c, m->e_mid1, buf[cur], H, false, buf[(cur + 1) & 3], buf[(cur + 2) & 3], buf[o2])) return -1;
+      RGM_CUDA_OK(cudaMemcpyAsync(buf[o], buf[o2], (size_t)nt * H * H * C * sizeof(__half), cudaMemcpyDeviceToDevice, st));
+    } else {
+      int t1 = -1, t2 = -1;  // two scratch buffers that are neither cur nor 3
+      for (int i = 0; i < 3; ++i)
+        if (i != cur) (t1 < 0 ? t1 : t2) = i;
+      if (run_res(c, m->e_mid1, buf[cur], H, false, buf[t1], buf[t2], buf[o])) return -1;
+    }
+    cur = o;
+  }
+  if (run_mid_attn(c, m->e_attn_norm, m->e_attn_q, m->e_attn_k, m->e_attn_v, m->e_attn_proj, buf, cur, H, C)) return -1;
+  cur = 0;
+  {
+    const int o = (cur + 3) & 3;
+    if (run_res(c, m->e_mid2, buf[cur], H, false, buf[(cur + 1) & 3], buf[(cur + 2) & 3], buf[o])) return -1;
+    cur = o;
+  }
+  // norm_out + swish, conv_out (C -> 2*zc, fp32 out, feature dim padded to 32), quant_conv 1x1 -> NCHW moments
+  if (gn_from_part(c, m->e_norm_out, H, false)) return -1;
+  __half* t = buf[(cur + 1) & 3];
+  RGM_CUDA_OK(launch_gn_apply(buf[cur], ab, t, nt, H * H, C, 1, st));
+  float* h32 = static_cast<float*>(L->attn_s.p);
+  {
+    const Conv& cv = m->e_cout;
+    GemmDesc d;
+    d.A = t;
+    d.n_img = nt;
+    d.H = H;
+    d.W = H;
+    d.C = cv.cin;
+    d.lda = cv.cin;
+    d.B = cv.w;
+    d.N = cv.cout_pad;
+    d.rows_b = cv.cout_pad;
+    d.conv = CONV_3x3;
+    d.epi = EPI_F32;
+    d.block_n = 32;
+    d.e.out = h32;
+    d.e.ldo = cv.cout_pad;
+    d.e.bias = cv.b;
+    d.e.alpha = 1.f;
+    RGM_VGEMM_OK(d);
+  }
+  const int zz = 2 * m->zc;
+  RGM_CUDA_OK(launch_vae_quant(h32, m->e_cout.cout_pad, m->q_w, m->q_b, moments + (long long)t0 * zz * H * H, nt, H * H,
+                               zz, st));
+  return 0;
+}
+
 }  // namespace
 }  // namespace rgm
 
@@ -392,6 +536,7 @@ int rgm_vae_create(rgm_vae** out, int ch, const int* ch_mult, int n_levels, int 
   m->nres = num_res_blocks;
   m->zc = z_channels;
   m->out_ch = out_ch;
+  m->in_ch = out_ch;  // the autoencoder's input and output are the same 3-channel piano roll (f8-all-onset.yaml:9-10)
   m->mult.assign(ch_mult, ch_mult + n_levels);
   for (int i = 0; i < n_levels; ++i)
     if ((ch * ch_mult[i]) % 128 != 0) {
@@ -444,6 +589,32 @@ int rgm_vae_load(rgm_vae* h, const char* key, const float* src, long long numel,
   if (numel != (long long)c.cout * c.cin * c.k * c.k)
     return set_error("rgm_vae_load: " + k + ": unexpected element count");
   return check_cuda(launch_pack_conv_weight(src, c.w, c.cout, c.cin, c.cout_pad, c.cin, c.kind, st), "rgm_vae_load");
+}
+
+int rgm_vae_encode(rgm_vae* h, const float* x, float* moments, int n, void* stream) {
+  if (rgm_check_device()) return -1;
+  if (!h || !x || !moments) return set_error("rgm_vae_encode: null argument");
+  Vae* m = reinterpret_cast<Vae*>(h);
+  if (n <= 0) return 0;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int chunk = m->chunk_tiles < n ? m->chunk_tiles : n;
+  long long maxc = 0;
+  for (int l = 0; l < m->n_levels; ++l) {
+    const long long hw = (long long)(16 << (m->n_levels - 1 - l)) * (16 << (m->n_levels - 1 - l));
+    const long long cmax = (long long)m->ch * m->mult[l < m->n_levels - 1 ? l + 1 : l];
+    maxc = std::max(maxc, hw * std::max(cmax, (long long)m->ch * m->mult[l]));
+  }
+  maxc = std::max(maxc, 4LL * 256 * m->block_in0);
+  Vae::Lane& L = m->lane[0];
+  for (int i = 0; i < 4; ++i) RGM_CUDA_OK(L.act[i].reserve((size_t)chunk * maxc * sizeof(__half)));
+  RGM_CUDA_OK(L.gnpart.reserve((size_t)chunk * maxc / 8 + 1024));
+  RGM_CUDA_OK(L.abbuf.reserve((size_t)chunk * 512 * sizeof(float2) * 2));
+  RGM_CUDA_OK(L.attn_s.reserve((size_t)chunk * 256 * 256 * sizeof(float)));
+  for (int t0 = 0; t0 < n; t0 += chunk) {
+    const int nt = (n - t0) < chunk ? (n - t0) : chunk;
+    if (encode_chunk(m, &L, x, moments, t0, nt, st) != 0) return -1;
+  }
+  return 0;
 }
 
 int rgm_vae_decode_latents(rgm_vae* h, const float* lat, float scale_factor, float* roll, int n_cand, int Hlat,

@@ -6,9 +6,9 @@ GaussianDiffusion.__init__ tables :138-189, q_sample :207-226, q_posterior_mean_
 :252-357, _predict_xstart_from_eps :359-364, _predict_eps_from_xstart :376-380, condition_mean :387-465 (classifier
 branch), condition_score :467-489, scg_sample :491-633, p_sample :635-735, p_sample_loop(_progressive) :737-879,
 ddim_sample :881-976, ddim_sample_loop(_progressive) :1016-1143, and the module helpers _extract_into_tensor :1331,
-_decode :1347, _extract_rule :1361, guide_schedule :1398.  Not on this path (raise NotImplementedError): training
-losses, bpd evaluation, DDIM reverse sampling, _encode (VAE encoder) and the DPS branch of condition_mean, which needs
-autograd through the denoiser.
+_decode :1347, _extract_rule :1361, guide_schedule :1398.  _encode :1382 (VAE encoder, for scripts/edit.py).  Not on this path
+(raise NotImplementedError): training losses, bpd evaluation, DDIM reverse sampling and the DPS branch of
+condition_mean, which needs autograd through the denoiser.
 
 What differs from the reference is only HOW a step runs:
   * the schedule tables are cast to fp32 once per device (same float64 -> index -> .float() values as
@@ -115,8 +115,15 @@ def _extract_rule(rule_name, pred_xstart):
     return FUNC_DICT[rule_name](pred_xstart)
 
 
-def _encode(*a, **k):
-    raise NotImplementedError("_encode needs the VAE encoder, which is not on the B200 sampling path (SURVEY.md 8f)")
+def _encode(pred_xstart, embed_model, scale_factor=1.):
+    """reference :1382-1395: piano roll [B, 3, 128, L] -> latent [B, 4, L/8, 16] (posterior mean * scale_factor)."""
+    h, w = pred_xstart.shape[-2], pred_xstart.shape[-1]
+    seq_len = w // h
+    micro = th.concat(th.chunk(pred_xstart, seq_len, dim=-1), dim=0)  # 1st second for all batch, 2nd second, ...
+    micro = embed_model.encode_save(micro, range_fix=False)
+    z = th.chunk(micro, 2, dim=1)[0] if micro.shape[1] == 8 else micro
+    z = th.concat(th.chunk(z, seq_len, dim=0), dim=-1)
+    return z.permute(0, 1, 3, 2) * scale_factor
 
 
 _TABLES = ("betas", "alphas_cumprod", "alphas_cumprod_prev", "sqrt_alphas_cumprod", "sqrt_one_minus_alphas_cumprod",

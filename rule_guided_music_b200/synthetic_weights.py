@@ -100,6 +100,58 @@ def vae_decoder_layout(ch=128, ch_mult=(1, 2, 2, 4), num_res_blocks=2, z_channel
     return L
 
 
+def vae_encoder_layout(ch=128, ch_mult=(1, 2, 2, 4), num_res_blocks=2, z_channels=4, in_channels=3):
+    """(name, kind, cin, cout) for every parameterised layer of Encoder + quant_conv, in forward order
+    (model.py:342-433, klvae_pedal.py:60-63)."""
+    L = [("encoder.conv_in", "conv3", in_channels, ch)]
+
+    def res(prefix, cin, cout):
+        L.append((prefix + ".norm1", "norm", cin, cin))
+        L.append((prefix + ".conv1", "conv3", cin, cout))
+        L.append((prefix + ".norm2", "norm", cout, cout))
+        L.append((prefix + ".conv2", "conv3", cout, cout))
+        if cin != cout:
+            L.append((prefix + ".nin_shortcut", "conv1", cin, cout))
+
+    block_in = ch
+    for lvl in range(len(ch_mult)):
+        block_out = ch * ch_mult[lvl]
+        for b in range(num_res_blocks):
+            res(f"encoder.down.{lvl}.block.{b}", block_in, block_out)
+            block_in = block_out
+        if lvl != len(ch_mult) - 1:
+            L.append((f"encoder.down.{lvl}.downsample.conv", "conv3", block_in, block_in))
+    res("encoder.mid.block_1", block_in, block_in)
+    L.append(("encoder.mid.attn_1.norm", "norm", block_in, block_in))
+    for n in ("q", "k", "v", "proj_out"):
+        L.append((f"encoder.mid.attn_1.{n}", "conv1", block_in, block_in))
+    res("encoder.mid.block_2", block_in, block_in)
+    L.append(("encoder.norm_out", "norm", block_in, block_in))
+    L.append(("encoder.conv_out", "conv3", block_in, 2 * z_channels))
+    L.append(("quant_conv", "conv1", 2 * z_channels, 2 * z_channels))
+    return L
+
+
+def _fill(layout, g):
+    sd = {}
+    for name, kind, cin, cout in layout:
+        if kind == "norm":
+            sd[name + ".weight"] = 1.0 + 0.1 * torch.randn(cin, generator=g)
+            sd[name + ".bias"] = 0.1 * torch.randn(cin, generator=g)
+        else:
+            k = 3 if kind == "conv3" else 1
+            bound = 1.0 / math.sqrt(cin * k * k)
+            sd[name + ".weight"] = (torch.rand(cout, cin, k, k, generator=g) * 2 - 1) * bound
+            sd[name + ".bias"] = (torch.rand(cout, generator=g) * 2 - 1) * bound
+    return sd
+
+
+def make_vae_encoder_state_dict(seed=2, **cfg):
+    """Encoder + quant_conv weights (separate generator from the decoder's, so the decoder tensors and every golden
+    vector made from them are unchanged)."""
+    return _fill(vae_encoder_layout(**cfg), torch.Generator(device="cpu").manual_seed(seed))
+
+
 def make_vae_state_dict(seed=1, **cfg):
     """Decoder + post_quant_conv weights, PyTorch-default-like scale (uniform +-1/sqrt(fan_in)), GroupNorm affine
     perturbed away from (1, 0) so the affine path is exercised."""

@@ -3,9 +3,10 @@
 Only what the sampling path calls is here: construction from the reference's ``ddconfig`` (the decoder fields of
 taming-transformers/configs/pr/kl/f8-all-onset.yaml:5-16), ``init_from_ckpt`` / ``load_state_dict`` with the
 reference's checkpoint keys (``decoder.*``, ``post_quant_conv.*``; encoder/loss keys are ignored like strict=False),
-``.to(device)``, ``.eval()`` and ``decode(z)``.  ``decode_latents`` is the fused form of
-gaussian_diffusion._decode (re-tiling + decode + roll assembly) that the native sampler uses.  The encoder
-(``encode`` / ``encode_save``) is not on this path and raises.
+``.to(device)``, ``.eval()``, ``decode(z)`` and -- for scripts/edit.py, which encodes the ground-truth roll once per
+run through gaussian_diffusion._encode -- ``encode_save(x)`` / ``encode(x)`` (klvae_pedal.py:60-78, checkpoint keys
+``encoder.*``, ``quant_conv.*``).  ``decode_latents`` is the fused form of gaussian_diffusion._decode (re-tiling +
+decode + roll assembly) that the native sampler uses.
 """
 import ctypes
 
@@ -41,7 +42,7 @@ class AutoencoderKL:
 
     def load_state_dict(self, state_dict, strict=True):
         for k, v in state_dict.items():
-            if k.startswith("decoder.") or k.startswith("post_quant_conv."):
+            if k.startswith(("decoder.", "post_quant_conv.", "encoder.", "quant_conv.")):
                 self._host_sd[k] = v.detach().to(torch.float32)
         unexpected = self._push(self._host_sd) if self._h is not None else []
         return [], unexpected
@@ -129,7 +130,45 @@ class AutoencoderKL:
         # a tile is [pitch, time]; decode_latents takes [time, pitch] like the sampler's latents
         return self.decode_latents(z.permute(0, 1, 3, 2), 1.0)
 
-    def encode(self, *a, **k):
-        raise NotImplementedError("the VAE encoder is not on the B200 sampling path (SURVEY.md section 8f)")
+    def encode_save(self, x, range_fix=False):
+        """x [n, 3, 128, 128] in [-1, 1] -> moments [n, 2*z_channels, 16, 16] (mean | logvar)  (klvae_pedal.py:60-68)."""
+        if self._h is None:
+            self.to(x.device)
+        n, c, H, W = x.shape
+        if c != self.ddconfig["in_channels"] or H != 128 or W != 128:
+            raise _lib.RgmError(f"encode_save: expected [n,{self.ddconfig['in_channels']},128,128], got {tuple(x.shape)}")
+        if not any(k.startswith("encoder.") for k in self._host_sd):
+            raise _lib.RgmError("encode_save: no encoder.* weights were loaded into this AutoencoderKL")
+        xin = x.contiguous().float()
+        zz = 2 * self.ddconfig["z_channels"]
+        moments = torch.empty(n, zz, 16, 16, device=xin.device, dtype=torch.float32)
+        with torch.cuda.device(self._device):
+            _lib.call("rgm_vae_encode", self._h, _lib.ptr(xin), _lib.ptr(moments), n, _lib.stream_ptr())
+        if range_fix:
+            mean, logvar = torch.chunk(moments, 2, dim=1)
+            moments = torch.concat((torch.sigmoid(mean) * 2 - 1, logvar), dim=1)
+        return moments
 
-    encode_save = encode
+    def encode(self, x, range_fix=False):
+        """-> DiagonalGaussianDistribution over the latent (klvae_pedal.py:70-78)."""
+        return DiagonalGaussianDistribution(self.encode_save(x, range_fix=range_fix))
+
+
+class DiagonalGaussianDistribution:
+    """taming/modules/distributions/distributions.py:24-62 (the parts sampling uses: mean, logvar clamp, sample, mode)."""
+
+    def __init__(self, parameters, deterministic=False):
+        self.parameters = parameters
+        self.mean, self.logvar = torch.chunk(parameters, 2, dim=1)
+        self.logvar = torch.clamp(self.logvar, -30.0, 20.0)
+        self.deterministic = deterministic
+        self.std = torch.exp(0.5 * self.logvar)
+        self.var = torch.exp(self.logvar)
+        if self.deterministic:
+            self.var = self.std = torch.zeros_like(self.mean)
+
+    def sample(self):
+        return self.mean + self.std * torch.randn(self.mean.shape).to(device=self.parameters.device)
+
+    def mode(self):
+        return self.mean

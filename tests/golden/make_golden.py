@@ -28,7 +28,7 @@ from guided_diffusion import respace as rrespace  # noqa: E402
 from guided_diffusion.condition_functions import model_fn  # noqa: E402
 from guided_diffusion.script_util import create_diffusion as _create_diffusion  # noqa: E402
 from music_rule_guidance.rule_maps import FUNC_DICT, LOSS_DICT  # noqa: E402
-from taming.modules.diffusionmodules.model import Decoder  # noqa: E402
+from taming.modules.diffusionmodules.model import Decoder, Encoder  # noqa: E402
 
 from oracle import weights as ow  # noqa: E402
 import golden_inputs as gi  # noqa: E402
@@ -146,6 +146,27 @@ def golden_vae():
     save("vae", **out)
 
 
+def golden_vae_enc():
+    """Encoder + quant_conv of the reference (model.py:342-433, klvae_pedal.py:60-68) and gaussian_diffusion._encode."""
+    sd = ow.make_vae_encoder_state_dict(seed=gi.VAE_ENC_SEED)
+    enc = Encoder(**ow.VAE_DDCONFIG)
+    qc = torch.nn.Conv2d(8, 8, 1)
+    enc.load_state_dict({k[len("encoder."):]: v for k, v in sd.items() if k.startswith("encoder.")}, strict=True)
+    qc.load_state_dict({k[len("quant_conv."):]: v for k, v in sd.items() if k.startswith("quant_conv.")}, strict=True)
+
+    class Embed:  # AutoencoderKL.encode_save with range_fix=False (klvae_pedal.py:60-68)
+        @staticmethod
+        def encode_save(x, range_fix=False):
+            assert not range_fix
+            return qc(enc(x))
+
+    rolls = gi.vae_rolls()
+    tiles = torch.cat(torch.chunk(rolls, rolls.shape[-1] // 128, dim=-1), dim=0)
+    out = {"moments": Embed.encode_save(tiles).numpy(),
+           "encode_latents": gd._encode(rolls, Embed, scale_factor=gi.SCALE_FACTOR).numpy()}
+    save("vae_enc", **out)
+
+
 def golden_sampler():
     """Short guided trajectories through the reference's own loops (seeded torch CPU RNG = shared noise stream)."""
     embed = build_ref_vae()
@@ -252,6 +273,6 @@ def golden_sampler_ext():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["schedule", "rules", "dit", "vae", "sampler", "sampler_ext"]
+    which = sys.argv[1:] or ["schedule", "rules", "dit", "vae", "vae_enc", "sampler", "sampler_ext"]
     for w in which:
         globals()["golden_" + w]()

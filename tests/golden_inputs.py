@@ -91,6 +91,25 @@ def vae_tiles(n=2):
     return torch.randn(n, 4, 16, 16, generator=g)
 
 
+VAE_ENC_SEED = 2
+
+
+def vae_rolls(B=2, L=256):
+    """Piano-roll-like encoder input [B,3,128,L] in [-1,1]: silence (-1) with sparse held notes / onsets / pedal."""
+    g = torch.Generator(device="cpu").manual_seed(23)
+    r = -torch.ones(B, 3, 128, L)
+    for b in range(B):
+        for _ in range(40):
+            p = int(torch.randint(21, 109, (1,), generator=g))
+            t0 = int(torch.randint(0, L - 8, (1,), generator=g))
+            d = int(torch.randint(2, 40, (1,), generator=g))
+            v = float(torch.rand(1, generator=g)) * 1.6 - 0.6
+            r[b, 0, p, t0:t0 + d] = v
+            r[b, 1, p, t0] = v
+        r[b, 2, :, 32 * b:32 * b + 64] = 0.3
+    return r + 0.01 * torch.randn(B, 3, 128, L, generator=g)
+
+
 def vae_latents(B=2, H=32):
     g = torch.Generator(device="cpu").manual_seed(22)
     return torch.randn(B, 4, H, 16, generator=g) * SCALE_FACTOR

@@ -22,10 +22,12 @@ def native_dit(cfg, device):
     return m, sd
 
 
-def native_vae(device):
+def native_vae(device, encoder=False):
     from rule_guided_music_b200.taming.models.klvae_pedal import AutoencoderKL
 
     sd = ow.make_vae_state_dict(seed=gi.VAE_SEED)
+    if encoder:
+        sd.update(ow.make_vae_encoder_state_dict(seed=gi.VAE_ENC_SEED))
     v = AutoencoderKL(ddconfig=ow.VAE_DDCONFIG, embed_dim=4)
     v.load_state_dict(sd, strict=False)
     v.to(device).eval()

@@ -44,7 +44,7 @@ def _pack(w, kind, cin_pad=None, cout_pad=None):
     cout, cin = w.shape[:2]
     cin_pad = cin_pad or cin
     cout_pad = cout_pad or cout
-    taps = {0: 1, 1: 9, 2: 4}[kind]
+    taps = {0: 1, 1: 9, 2: 4, 3: 9}[kind]
     npar = 4 if kind == 2 else 1
     out = torch.empty(npar * cout_pad * taps * cin_pad, device=w.device, dtype=torch.float16)
     _lib.call("rgm_pack_conv_weight", _lib.ptr(w.contiguous()), _lib.ptr(out), cout, cin, cout_pad, cin_pad, kind,
@@ -54,8 +54,8 @@ def _pack(w, kind, cin_pad=None, cout_pad=None):
 
 def _conv(x_nhwc16, wp, bias, cout, kind, resid=None, bn=0, gn_part=None):
     n, H, W, cin = x_nhwc16.shape
-    s = 2 if kind == 2 else 1
-    out = torch.empty(n, H * s, W * s, cout, device=x_nhwc16.device, dtype=torch.float16)
+    Ho, Wo = (H * 2, W * 2) if kind == 2 else ((H // 2, W // 2) if kind == 3 else (H, W))
+    out = torch.empty(n, Ho, Wo, cout, device=x_nhwc16.device, dtype=torch.float16)
     _lib.call("rgm_conv_f16", _lib.ptr(x_nhwc16), _lib.ptr(wp), _lib.ptr(bias), _lib.ptr(resid), _lib.ptr(out), n, H,
               W, cin, cout, kind, bn, _lib.ptr(gn_part), _lib.stream_ptr())
     return out
@@ -70,6 +70,9 @@ def _conv(x_nhwc16, wp, bias, cout, kind, resid=None, bn=0, gn_part=None):
     (2, 16, 64, 128, 2),
     (2, 64, 128, 256, 2),
     (3, 32, 256, 128, 0),
+    (2, 128, 128, 128, 3),   # Downsample (stride 2, pad right/bottom): the three encoder shapes
+    (3, 64, 256, 256, 3),
+    (5, 32, 256, 256, 3),
 ])
 def test_conv(cuda, n, H, cin, cout, kind):
     g = torch.Generator(device="cpu").manual_seed(n * 1000 + H + cin + cout + kind)
@@ -83,7 +86,10 @@ def test_conv(cuda, n, H, cin, cout, kind):
     xin = x.float()
     if kind == 2:
         xin = F.interpolate(xin, scale_factor=2.0, mode="nearest")
-    ref = F.conv2d(xin, w.half().float(), bias, padding=k // 2)
+    if kind == 3:
+        ref = F.conv2d(F.pad(xin, (0, 1, 0, 1)), w.half().float(), bias, stride=2)
+    else:
+        ref = F.conv2d(xin, w.half().float(), bias, padding=k // 2)
     torch.cuda.synchronize()
     err = (out - ref).abs().max().item()
     tol = (4e-3 if kind == 2 else 2e-3) * ref.abs().max().item()

@@ -134,6 +134,20 @@ def test_vae_against_reference():
     np.testing.assert_allclose(roll[:, :, ::4, ::4].numpy(), g["decode_latents_sub4"], atol=2e-5, rtol=1e-4)
 
 
+def test_vae_encoder_against_reference():
+    """Encoder + quant_conv and _encode against the unmodified reference's outputs."""
+    g = _load("vae_enc")
+    sd = ow.make_vae_encoder_state_dict(seed=gi.VAE_ENC_SEED)
+    rolls = gi.vae_rolls()
+    tiles = torch.cat(torch.chunk(rolls, rolls.shape[-1] // 128, dim=-1), dim=0)
+    with torch.no_grad():
+        moments = ovae.vae_encode(sd, tiles).numpy()
+        lat = ovae.encode_rolls(sd, rolls, gi.SCALE_FACTOR).numpy()
+    assert moments.shape == (4, 8, 16, 16) and lat.shape == (2, 4, 32, 16)
+    np.testing.assert_allclose(moments, g["moments"], atol=2e-5, rtol=1e-4)
+    np.testing.assert_allclose(lat, g["encode_latents"], atol=2e-5, rtol=1e-4)
+
+
 def oracle_model_fn(sd, cfg):
     kw = _dit_kw(cfg)
 

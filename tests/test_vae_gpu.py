@@ -52,3 +52,49 @@ def test_decode_many_tiles_vs_oracle(cuda):
         ref = ovae.decode_latents(sd, lat, 1.3)
     out = vae.decode_latents(lat.to(cuda), 1.3).cpu()
     assert gpu_util.rel_l2(out, ref) < 5e-3
+
+
+# ---- encoder (scripts/edit.py: gaussian_diffusion._encode of the ground-truth roll) -------------------------------------
+GOLD_ENC = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "vae_enc.npz"))
+
+
+def test_encode_matches_reference(cuda):
+    """Encoder + quant_conv (stride-2 implicit-GEMM Downsample, fp32 stem and tail) vs the reference's moments, and
+    _encode's re-tiling vs the reference's latents.  Same precision policy and bar as the decoder (5e-3 rel L2)."""
+    from rule_guided_music_b200.guided_diffusion.gaussian_diffusion import _encode
+
+    vae, _ = gpu_util.native_vae(cuda, encoder=True)
+    rolls = gi.vae_rolls()
+    tiles = torch.cat(torch.chunk(rolls, rolls.shape[-1] // 128, dim=-1), dim=0)
+    moments = vae.encode_save(tiles.to(cuda)).cpu()
+    ref = torch.from_numpy(GOLD_ENC["moments"])
+    assert moments.shape == ref.shape
+    assert gpu_util.rel_l2(moments, ref) < 5e-3, gpu_util.rel_l2(moments, ref)
+    lat = _encode(rolls.to(cuda), vae, scale_factor=gi.SCALE_FACTOR).cpu()
+    ref_lat = torch.from_numpy(GOLD_ENC["encode_latents"])
+    assert lat.shape == ref_lat.shape
+    assert gpu_util.rel_l2(lat, ref_lat) < 5e-3
+    post = vae.encode(tiles.to(cuda))
+    assert torch.equal(post.mode().cpu(), moments[:, :4])
+    assert post.sample().shape == (4, 4, 16, 16)
+
+
+def test_encode_chunked_equals_unchunked_and_oracle(cuda, monkeypatch):
+    vae, sd = gpu_util.native_vae(cuda, encoder=True)
+    g = torch.Generator(device="cpu").manual_seed(31)
+    x = (torch.rand(5, 3, 128, 128, generator=g) * 2 - 1)
+    with torch.no_grad():
+        ref = ovae.vae_encode(sd, x)
+    out = vae.encode_save(x.to(cuda)).cpu()
+    assert gpu_util.rel_l2(out, ref) < 5e-3
+    monkeypatch.setenv("RGM_VAE_CHUNK", "2")
+    vae2, _ = gpu_util.native_vae(cuda, encoder=True)
+    assert torch.equal(vae2.encode_save(x.to(cuda)).cpu(), out)
+
+
+def test_encode_without_encoder_weights_raises(cuda):
+    from rule_guided_music_b200 import _lib
+
+    vae, _ = gpu_util.native_vae(cuda)
+    with pytest.raises(_lib.RgmError):
+        vae.encode_save(torch.zeros(1, 3, 128, 128, device=cuda))

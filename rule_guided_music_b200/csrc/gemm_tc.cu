@@ -245,7 +245,8 @@ cudaError_t launch_gemm(const GemmDesc& d, cudaStream_t stream, std::string* err
   }
   p.epi = d.e;
   p.trace = d.trace;
-  if (const char* bn = getenv("RGM_GEMM_BAND")) p.band_n = atoi(bn);  // experiment knob, read per launch
+  if (const char* bn = getenv("RGM_GEMM_BAND")) p.band_n = atoi(bn);  // experiment knobs, read per launch
+  if (const char* dbg = getenv("RGM_GEMM_DEBUG")) p.debug = atoi(dbg);
   if (const char* tp = getenv("RGM_DEBUG_TRACE_PTR")) {  // development aid: trace every launch with a given epilogue
     const char* te = getenv("RGM_DEBUG_TRACE_EPI");
     if (te && atoi(te) == d.epi && (!getenv("RGM_DEBUG_TRACE_N") || atoi(getenv("RGM_DEBUG_TRACE_N")) == d.N))

@@ -8,6 +8,8 @@
 // with the tap's (dy, dx) shift -- out-of-image pixels are zero-filled by TMA, which IS the conv's zero padding.
 // A plain linear layer is the degenerate case n_img = 1, H = 1, W = M, one tap.
 #pragma once
+#include <type_traits>
+
 #include "ptx.cuh"
 
 namespace rgm {
@@ -63,6 +65,8 @@ struct GemmParams {
   int tiles_per_img, tiles_per_row, bh, bw;
   int b_batched;              // B's third coordinate follows the image index (batched GEMM)
   int slots_per_par;          // GroupNorm partial slots (128-row groups) per output parity = ceil(M / 128)
+  int debug;                  // development aid (pair kernel): bit 0 = skip the TMA loads, bit 1 = skip the epilogue,
+                              // bit 2 = epilogue reads TMEM but computes / stores nothing, bit 3 = EPI_F16 computes but does not store
   int band_n;                 // pair kernel rasterisation: feature-tile pairs per band (0 = all: feature pairs fastest)
   int in_stride;              // 1, or 2 for the stride-2 Downsample conv: input pixel = in_stride * output pixel + tap
   signed char tap_dy[4][9];
@@ -112,29 +116,47 @@ __device__ __forceinline__ float apply_act(float x) {
   else return x;
 }
 
-// Fast column loops: the 32 rows of the round are all valid and their destination rows are equally spaced
-// (`ostride` elements apart), so addresses advance by pointer increments -- about ten instructions per element.
-template <int ACT, bool RESID>
-__device__ __forceinline__ void cols_f16_fast(const float (&val)[32], __half* op, const __half* rp, long long ostride,
-                                              long long rstride, float alpha, float bias, float& s, float& q) {
+// Fast column loops: the 32 rows of the round are all valid and their destination rows are equally spaced (`os`
+// elements apart).  Every instruction issued here costs tensor-pipe time: with the epilogue switched off the same
+// mainloop runs 30-40 % faster (profiles/r1_probe_bound.txt; tile time = MMA time + epilogue issue slots per SM
+// sub-partition), so the loops are written for instruction count: the row stride is a template constant for the strides
+// the path uses (stores and residual loads then take immediate offsets -- no address arithmetic at all), and the
+// GroupNorm sums are taken from the fp32 value before rounding (no convert-back; the reference's statistics are fp32
+// as well).  5 instructions per element (FFMA, F2F, STG, FADD, FFMA) instead of 10.
+template <int ACT, bool RESID, int OS>
+__device__ __forceinline__ void cols_f16_fast(const float (&val)[32], __half* op, const __half* rp, int os_dyn,
+                                              float alpha, float bias, float& s, float& q, bool nostore) {
+  const int os = OS > 0 ? OS : os_dyn;
   // The residual may alias the output (ResnetBlock shortcut written in place), so the compiler will not move a
   // residual load above an earlier store: issue all 32 loads first, then the dependent stores (measured: a
   // load -> store chain costs ~600 cycles per row).
   __half rv[32];
   if constexpr (RESID) {
 #pragma unroll
-    for (int j = 0; j < 32; ++j) rv[j] = rp[(long long)j * rstride];
+    for (int j = 0; j < 32; ++j) rv[j] = rp[j * os];
   }
 #pragma unroll
   for (int j = 0; j < 32; ++j) {
     float x = apply_act<ACT>(fmaf(val[j], alpha, bias));
     if constexpr (RESID) x += __half2float(rv[j]);
-    const __half h = __float2half_rn(x);
-    *op = h;
-    op += ostride;
-    const float f = __half2float(h);  // statistics of exactly the value the next layer reads
-    s += f;
-    q = fmaf(f, f, q);
+    if (!nostore) op[j * os] = __float2half_rn(x);  // (nostore: bound analysis only, GemmParams::debug bit 3)
+    s += x;
+    q = fmaf(x, x, q);
+  }
+}
+
+// row-stride dispatch: the strides of the VAE levels (128 / 256 / 512 channels, x2 for the upsample scatter) and of the
+// DiT MLP (4608); anything else takes the dynamic-stride instantiation (one IMAD.WIDE per element)
+template <int ACT, bool RESID>
+__device__ __forceinline__ void cols_f16_dispatch(const float (&val)[32], __half* op, const __half* rp, int os,
+                                                  float alpha, float bias, float& s, float& q, bool nostore) {
+  switch (os) {
+    case 128: cols_f16_fast<ACT, RESID, 128>(val, op, rp, os, alpha, bias, s, q, nostore); break;
+    case 256: cols_f16_fast<ACT, RESID, 256>(val, op, rp, os, alpha, bias, s, q, nostore); break;
+    case 512: cols_f16_fast<ACT, RESID, 512>(val, op, rp, os, alpha, bias, s, q, nostore); break;
+    case 1024: cols_f16_fast<ACT, RESID, 1024>(val, op, rp, os, alpha, bias, s, q, nostore); break;
+    case 4608: cols_f16_fast<ACT, RESID, 4608>(val, op, rp, os, alpha, bias, s, q, nostore); break;
+    default: cols_f16_fast<ACT, RESID, 0>(val, op, rp, os, alpha, bias, s, q, nostore); break;
   }
 }
 
@@ -154,19 +176,19 @@ __device__ __forceinline__ void epilogue_cols_core(const GemmParams& p, const fl
 
   if constexpr (EPI == EPI_F16) {
     // s, q: running GroupNorm sums of this thread's feature over the rows it has stored (written by the caller)
-    if (uniform_rows && e.addtab == nullptr) {
+    if (uniform_rows && e.addtab == nullptr && (e.resid == nullptr || e.ldr == e.ldo)) {
       __half* op = static_cast<__half*>(e.out) + (long long)orow0 * e.ldo + n;
-      const long long ostride = (long long)orow_step * e.ldo;
+      const int os = orow_step * e.ldo;
+      const bool ns = (p.debug & 8) != 0;
       if (e.resid != nullptr) {
         const __half* rp = e.resid + (long long)orow0 * e.ldr + n;
-        const long long rstride = (long long)orow_step * e.ldr;
-        if (e.act == ACT_NONE) cols_f16_fast<ACT_NONE, true>(val, op, rp, ostride, rstride, e.alpha, bias, s, q);
-        else if (e.act == ACT_SILU) cols_f16_fast<ACT_SILU, true>(val, op, rp, ostride, rstride, e.alpha, bias, s, q);
-        else cols_f16_fast<ACT_GELU_TANH, true>(val, op, rp, ostride, rstride, e.alpha, bias, s, q);
+        if (e.act == ACT_NONE) cols_f16_dispatch<ACT_NONE, true>(val, op, rp, os, e.alpha, bias, s, q, ns);
+        else if (e.act == ACT_SILU) cols_f16_fast<ACT_SILU, true, 0>(val, op, rp, os, e.alpha, bias, s, q, ns);
+        else cols_f16_fast<ACT_GELU_TANH, true, 0>(val, op, rp, os, e.alpha, bias, s, q, ns);
       } else {
-        if (e.act == ACT_NONE) cols_f16_fast<ACT_NONE, false>(val, op, nullptr, ostride, 0, e.alpha, bias, s, q);
-        else if (e.act == ACT_SILU) cols_f16_fast<ACT_SILU, false>(val, op, nullptr, ostride, 0, e.alpha, bias, s, q);
-        else cols_f16_fast<ACT_GELU_TANH, false>(val, op, nullptr, ostride, 0, e.alpha, bias, s, q);
+        if (e.act == ACT_NONE) cols_f16_dispatch<ACT_NONE, false>(val, op, nullptr, os, e.alpha, bias, s, q, ns);
+        else if (e.act == ACT_SILU) cols_f16_fast<ACT_SILU, false, 0>(val, op, nullptr, os, e.alpha, bias, s, q, ns);
+        else cols_f16_dispatch<ACT_GELU_TANH, false>(val, op, nullptr, os, e.alpha, bias, s, q, ns);
       }
     } else {
       // general path: ragged last rows, 16-pixel-wide upsample rows, gathered row-vector add
@@ -179,11 +201,9 @@ __device__ __forceinline__ void epilogue_cols_core(const GemmParams& p, const fl
           if (e.act == ACT_SILU) x = silu_f(x);
           else if (e.act == ACT_GELU_TANH) x = gelu_tanh_f(x);
           if (e.resid) x += __half2float(e.resid[(long long)orow * e.ldr + n]);
-          const __half h = __float2half_rn(x);
-          static_cast<__half*>(e.out)[(long long)orow * e.ldo + n] = h;
-          const float f = __half2float(h);
-          s += f;
-          q += f * f;
+          static_cast<__half*>(e.out)[(long long)orow * e.ldo + n] = __float2half_rn(x);
+          s += x;
+          q = fmaf(x, x, q);
         }
       }
     }
@@ -214,11 +234,16 @@ __device__ __forceinline__ void epilogue_cols_core(const GemmParams& p, const fl
     const float g = __ldg(e.gate + (long long)(row0 / e.rows_per_sample) * e.gate_ld + n);
     if (uniform_rows) {
       float* px = static_cast<float*>(e.out) + (long long)orow0 * e.ldo + n;
-      float xin[32];
+      auto rmw = [&](auto LD) {  // LD: compile-time row stride (immediate offsets) or 0 = e.ldo
+        const int ld = decltype(LD)::value > 0 ? decltype(LD)::value : e.ldo;
+        float xin[32];
 #pragma unroll
-      for (int j = 0; j < 32; ++j) xin[j] = px[(long long)j * e.ldo];
+        for (int j = 0; j < 32; ++j) xin[j] = px[j * ld];
 #pragma unroll
-      for (int j = 0; j < 32; ++j) px[(long long)j * e.ldo] = fmaf(g, val[j] + bias, xin[j]);
+        for (int j = 0; j < 32; ++j) px[j * ld] = fmaf(g, val[j] + bias, xin[j]);
+      };
+      if (e.ldo == 1152) rmw(std::integral_constant<int, 1152>{});
+      else rmw(std::integral_constant<int, 0>{});
     } else {
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
@@ -254,16 +279,25 @@ __device__ __forceinline__ void epilogue_cols_core(const GemmParams& p, const fl
     const float dc = rot ? stp.x : 1.f, ds = rot ? stp.y : 0.f;
     const float sgn = (d & 1) ? 1.f : -1.f;
     const int nrows = p.M - row0 < 32 ? p.M - row0 : 32;
+    // y = x cos + sgn * partner * sin with the sign folded into the sine (ss = sgn * sin rotates like sin does when
+    // the step's sine carries the same sign twice: ss' = ss dc + c (sgn ds); c' = c dc - ss (sgn ds))
+    float ss = sgn * sn;
+    const float dss = sgn * ds;
+    auto rows = [&](auto DP, bool full) {  // DP: compile-time row pitch of q / k (immediate store offsets) or 0
+      const int dp = decltype(DP)::value > 0 ? decltype(DP)::value : e.dh_pad;
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      const float x = val[j] + bias;
-      const float px = __shfl_xor_sync(0xffffffffu, x, 1);
-      const float y = fmaf(px * sgn, sn, x * c);
-      if (j < nrows) qp[(long long)j * e.dh_pad] = __float2half_rn(y);
-      const float c2 = fmaf(c, dc, -sn * ds);
-      sn = fmaf(sn, dc, c * ds);
-      c = c2;
-    }
+      for (int j = 0; j < 32; ++j) {
+        const float x = val[j] + bias;
+        const float px = __shfl_xor_sync(0xffffffffu, x, 1);
+        const float y = fmaf(px, ss, x * c);
+        if (full || j < nrows) qp[j * dp] = __float2half_rn(y);
+        const float c2 = fmaf(c, dc, -ss * dss);
+        ss = fmaf(ss, dc, c * dss);
+        c = c2;
+      }
+    };
+    if (e.dh_pad == 72 && nrows == 32) rows(std::integral_constant<int, 72>{}, true);
+    else rows(std::integral_constant<int, 0>{}, false);
   }
 }
 
@@ -590,6 +624,7 @@ __device__ __forceinline__ void sw_epilogue_tile(const GemmParams& p, uint32_t t
     uint32_t r[32];
     tmem_ld_32x32(taddr + c, r);
     tmem_ld_wait();
+    if (p.debug & 4) continue;  // bound analysis: TMEM reads only
     if constexpr (EPI == EPI_QKV_ROPE) {
       const int D = p.epi.heads * p.epi.dh;
       if (n_tile * SW_FEATS + quad * 32 >= 2 * D) {
@@ -909,11 +944,15 @@ gemm_sw2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
           const int dy = p.tap_dy[par][tap], dx = p.tap_dx[par][tap];
           for (int kc = 0; kc < p.kb_per_tap; ++kc) {
             mbar_wait(&empty_bar[stage], phase ^ 1);
-            if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * (SW2_W_BYTES + SW2_X_BYTES));
-            tma_load_4d_pair(smem_x + stage * SW2_X_BYTES, &tmap_x, &full_bar[stage], kc * GEMM_BLOCK_K, w0 + dx,
-                             h0 + dy, img);
-            tma_load_3d_pair(smem_w + stage * SW2_W_BYTES, &tmap_w, &full_bar[stage],
-                             (tap * p.kb_per_tap + kc) * GEMM_BLOCK_K, wrow, bz);
+            if (p.debug & 1) {  // bound analysis: MMAs on stale shared memory, no operand traffic
+              if (rank == 0) mbar_arrive(&full_bar[stage]);
+            } else {
+              if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * (SW2_W_BYTES + SW2_X_BYTES));
+              tma_load_4d_pair(smem_x + stage * SW2_X_BYTES, &tmap_x, &full_bar[stage], kc * GEMM_BLOCK_K, w0 + dx,
+                               h0 + dy, img);
+              tma_load_3d_pair(smem_w + stage * SW2_W_BYTES, &tmap_w, &full_bar[stage],
+                               (tap * p.kb_per_tap + kc) * GEMM_BLOCK_K, wrow, bz);
+            }
             if (++stage == SW2_STAGES) {
               stage = 0;
               phase ^= 1;
@@ -970,7 +1009,7 @@ gemm_sw2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       if (p.trace && blockIdx.x == 0 && warp == 2 && lane == 0) p.trace[(t / num_pairs) * 8 + 4] = clock64();
-      if (n_tile < p.num_n_tiles)
+      if (n_tile < p.num_n_tiles && !(p.debug & 2))
         sw_epilogue_tile<EPI>(p, tmem_base + acc * SW_ROWS, m_tile, n_tile, par, quad, rhalf, lane);
       tc_fence_before();
       __syncwarp();

@@ -7,7 +7,11 @@
 // S, write un-normalised P = exp2((s - max) * scale*log2e) as fp16 into a swizzled K-major smem tile, the MMA thread
 // runs O = P V into the TMEM columns S occupied, and the softmax warps scale O by 1/rowsum on the way out.
 // The two query tiles are software-pipelined: the tensor core computes S1 and P0 V while the softmax warps work on
-// tile 0 / tile 1, so the MUFU-bound softmax (128 x T exponentials per tile) overlaps the MMAs.
+// tile 0 / tile 1, so the softmax (128 x T exponentials per tile) overlaps the MMAs.
+// EIGHT softmax warps: warps w and w + 4 share a TMEM lane quadrant (the same 32 query rows) and each takes half of the
+// columns; they exchange their row maxima and row sums through shared memory under a 64-thread named barrier.  With
+// one warp per scheduler the softmax was a chain of exposed tcgen05.ld / MUFU / st.shared latencies (49 ms per step
+// against an 11 ms MUFU floor); two warps per scheduler overlap each other's latencies and halve the per-warp work.
 #include <atomic>
 #include <mutex>
 #include <unordered_map>
@@ -20,7 +24,12 @@ namespace rgm {
 
 namespace {
 
-constexpr int ATT_THREADS = 160;  // warp 0: TMA + MMA issue (+ TMEM owner); warps 1..4: softmax / epilogue
+constexpr int ATT_SOFTMAX_WARPS = 8;
+constexpr int ATT_THREADS = 32 + 32 * ATT_SOFTMAX_WARPS;  // warp 0: TMA + MMA issue (+ TMEM owner); warps 1..8: softmax / epilogue
+
+__device__ __forceinline__ void named_bar_sync(int id, int threads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
 
 struct AttnParams {
   int n_pairs;   // B * heads
@@ -72,6 +81,7 @@ attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
   uint64_t* bar_o = bars + 5;       // [2] O tile complete
   uint64_t* bar_done = bars + 7;    // epilogue has drained TMEM (128 arrivals)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  float* red = reinterpret_cast<float*>(bars + 10);  // [column half][row]: partner exchange of row max, then row sum
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
@@ -81,10 +91,10 @@ attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
     mbar_init(bar_load, 1);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&bar_s[i], 1);
-      mbar_init(&bar_p[i], 128);
+      mbar_init(&bar_p[i], 32 * ATT_SOFTMAX_WARPS);
       mbar_init(&bar_o[i], 1);
     }
-    mbar_init(bar_done, 128);
+    mbar_init(bar_done, 32 * ATT_SOFTMAX_WARPS);
     fence_barrier_init();
   }
   if (warp == 0) {
@@ -144,7 +154,10 @@ attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
       __syncwarp();
     } else {
       const int quad = warp & 3;                 // TMEM lane quadrant this warp may touch
+      const int half = (warp - 1) >> 2;          // which half of the columns (warps w and w + 4 share the rows)
       const int r = quad * 32 + lane;            // query row within the tile
+      const int cw = T >> 1;                     // columns per warp
+      const int c_lo = half * cw;
       float inv_sum[2] = {0.f, 0.f};
 #pragma unroll
       for (int m = 0; m < 2; ++m) {
@@ -153,19 +166,23 @@ attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
         tc_fence_after();
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + m * 256;
         float mx = -INFINITY;
-        for (int c = 0; c < T; c += 32) {
+        for (int c = c_lo; c < c_lo + cw; c += 32) {
           uint32_t v[32];
           tmem_ld_32x32(taddr + c, v);
           tmem_ld_wait();
 #pragma unroll
           for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
         }
+        red[half * 128 + r] = mx;
+        named_bar_sync(1 + quad, 64);
+        mx = fmaxf(mx, red[(half ^ 1) * 128 + r]);
+        named_bar_sync(1 + quad, 64);  // both maxima read: the slots are free for the sums
         // the single P buffer is read by the previous tile's P V MMAs: wait for them before overwriting it
         if (m > 0) mbar_wait(&bar_o[m - 1], ph);
         else if (p.n_tiles > 1) mbar_wait(&bar_s[1], ph);  // Q1 is staged in the P buffer until S1 is done
         const float mneg = -mx * p.scale_log2e;
         float sum = 0.f;
-        for (int c = 0; c < T; c += 32) {
+        for (int c = c_lo; c < c_lo + cw; c += 32) {
           uint32_t v[32];
           tmem_ld_32x32(taddr + c, v);
           tmem_ld_wait();
@@ -184,12 +201,15 @@ attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
 #pragma unroll
           for (int j = 0; j < 4; ++j) sts_v4(rowp + (((ch0 + j) ^ (r & 7)) << 4), pk[j]);
         }
-        inv_sum[m] = 1.0f / sum;
+        red[half * 128 + r] = sum;
         tc_fence_before();
         fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
         mbar_arrive(&bar_p[m]);
+        named_bar_sync(1 + quad, 64);
+        inv_sum[m] = 1.0f / (sum + red[(half ^ 1) * 128 + r]);
+        named_bar_sync(1 + quad, 64);  // both sums read before the next tile's maxima overwrite the slots
       }
-      // epilogue: O / rowsum -> out[b*T + row, head*dh + d]
+      // epilogue: O / rowsum -> out[b*T + row, head*dh + d]; the 16-column groups of O alternate between the two warps
       const int b = pair / p.heads, head = pair - b * p.heads;
 #pragma unroll
       for (int m = 0; m < 2; ++m) {
@@ -198,7 +218,7 @@ attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
         tc_fence_after();
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + m * 256;
         __half* orow = p.out + ((long long)b * T + m * 128 + r) * (p.heads * p.dh) + head * p.dh;
-        for (int c = 0; c < p.npv; c += 16) {
+        for (int c = half * 16; c < p.npv; c += 32) {
           uint32_t v[16];
           tmem_ld_32x16(taddr + c, v);
           tmem_ld_wait();
@@ -285,7 +305,7 @@ cudaError_t launch_attention(const __half* q, const __half* k, const __half* vt,
       !map2d(&mv, vt, T, (unsigned long long)B * heads * dh, 64, p.npv))
     return fail("attention: cuTensorMapEncodeTiled failed");
   const size_t smem = 1024 + p.nkb * 16384 + (size_t)p.nkb * T * 128 + (size_t)(T / 64) * p.npv * 128 +
-                      (size_t)(T / 64) * 16384 + 128;
+                      (size_t)(T / 64) * 16384 + 128 + 2 * 128 * sizeof(float);
   static size_t smem_set = 0;
   if (smem > smem_set) {
     cudaError_t e = cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -35,6 +35,16 @@ TARGET = [0.5, 0, 0, 0, 0.25, 0, 0, 0.25, 0, 0, 0, 0]
 GUIDANCE = SimpleNamespace(schedule=False, t_start=750, t_end=0, interval=1, method="scg", step_size=1.0, nn=False)
 
 
+def workload_config(B, N, world):
+    """The `config` object both arms print (the reference arm runs a bounded sample of this workload, see its
+    cpu_baseline.sample)."""
+    return {"workload": "config 3: DDIM(eta=1) respacing '256', SCG N=%d, pitch_hist, batch %d per GPU, DiTRotary_XL_8 "
+                        "random-init (adaLN/final re-randomised), 4x128x16" % (N, B),
+            "global_batch": B * world, "candidates": N,
+            "parallelism": "batch-sharded x%d, no per-step collective" % world,
+            "l2": "no flush: one step streams >100 GB of activations through HBM, far beyond the 126 MB L2"}
+
+
 def step_flops(B, N, tiles=8):
     return B * ((1 + N) * F_DIT + N * tiles * F_VAE_TILE)
 
@@ -117,12 +127,12 @@ def run_reference(args):
     cores = torch.get_num_threads()
     value, sec, scale = cpu_steps(args.steps, min(args.warmup, 1), B=1, N=1)
     sample = (f"oracle port of the reference step at B=1, N=1 (1+1 DiT forwards, 8 VAE tiles): {sec:.2f} s per sample "
-              f"step on {cores} threads, scaled x{scale:.0f} (algorithmic FLOPs) to B=64, N=16")
+              f"step on {cores} threads, scaled x{scale:.0f} (algorithmic FLOPs) to B=64, N=16; value counts B=64 batch-steps "
+              f"per second like the GPU arm's (the host's rate does not change with --gpus)")
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": sec * scale * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "config 3: DDIM(eta=1) respacing '256', SCG N=16, pitch_hist, batch 64, "
-                                   "DiTRotary_XL_8 random-init (adaLN/final re-randomised), 4x128x16"},
+            "config": workload_config(B_FULL, N_FULL, max(args.gpus, 1)),
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
@@ -280,11 +290,7 @@ def run_b200(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f16 operands, f32 accumulate/residual", "data": "synthetic",
-            "config": {"workload": "config 3: DDIM(eta=1) respacing '256', SCG N=%d, pitch_hist, batch %d per GPU, "
-                                   "DiTRotary_XL_8 random-init (adaLN/final re-randomised), 4x128x16" % (N, B),
-                       "global_batch": B * world, "candidates": N, "parallelism": "batch-sharded x%d, no per-step "
-                       "collective" % world,
-                       "l2": "no flush: one step streams >100 GB of activations through HBM, far beyond the 126 MB L2"},
+            "config": workload_config(B, N, world),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * 4 * 128 * 16 * 4,
                     "d2h_bytes_per_step": B * 4 * 128 * 16 * 4},
             "gpu_launches": int(launches),

@@ -54,6 +54,9 @@ class SpacedDiffusion(GaussianDiffusion):
                 self.timestep_map.append(i)
         kwargs["betas"] = np.array(new_betas)
         super().__init__(**kwargs)
+        # device copies of timestep_map, shared by every wrapper this diffusion hands out: a wrapper is built per call,
+        # and a fresh host->device copy per step would be a pageable transfer (illegal inside a graph capture)
+        self._dev_maps = {}
 
     def p_mean_variance(self, model, *args, **kwargs):
         return super().p_mean_variance(self._wrap_model(model), *args, **kwargs)
@@ -67,10 +70,6 @@ class SpacedDiffusion(GaussianDiffusion):
     def _wrap_model(self, model):
         if isinstance(model, _WrappedModel):
             return model
-        # the device copies of timestep_map are shared by every wrapper this diffusion hands out: a wrapper is built
-        # per call, and a fresh host->device copy per step would be a pageable transfer (illegal in a graph capture)
-        if not hasattr(self, "_dev_maps"):
-            self._dev_maps = {}
         return _WrappedModel(model, self.timestep_map, self.rescale_timesteps, self.original_num_steps,
                              maps=self._dev_maps)
 

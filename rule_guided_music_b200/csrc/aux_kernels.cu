@@ -4,10 +4,16 @@
 #include <atomic>
 
 #include "api_util.h"
+#include <cstdio>
+#include <cstdlib>
+
 #include "aux_kernels.h"
 #include "ptx.cuh"
 
 namespace rgm {
+
+// x * sigmoid(x) in 5 issue slots (ptx.cuh silu_f): the GroupNorm passes are ISSUE-bound, not MUFU- or HBM-bound.
+__device__ __forceinline__ float swish_fast(float v) { return silu_f(v); }
 
 namespace {
 std::atomic<unsigned long long> g_launches{0};
@@ -414,11 +420,13 @@ cudaError_t launch_gn_finalize(const float* part, const float* gamma, const floa
 // grid = (pixel chunks, images).  A thread owns ONE 8-channel vector position (its GroupNorm coefficients stay in
 // registers) and walks the image's pixels with a stride, three 16-byte loads in flight; a warp covers 512 contiguous
 // bytes per load.  One fp16 read and one fp16 write per element.
-// (__launch_bounds__(256, 6) caps the kernel at 42 registers so that one block fits beside a resident GEMM CTA --
-// 320 threads x 168 registers -- and the two VAE lanes really overlap HBM-bound and tensor-bound work on an SM)
-template <int SWISH>
-__global__ void __launch_bounds__(256, 6) gn_apply_kernel(const __half* __restrict__ x, const float2* __restrict__ ab,
-                                                       __half* __restrict__ y, int HW, int C) {
+// PIPE = 1 keeps the next batch's loads in flight while this batch is normalised and stored (64 registers, 4 blocks
+// per SM); PIPE = 0 is the 40-register form that fits beside a resident GEMM CTA.  Measured: 4.9 vs 4.7 TB/s, and the
+// two-lane decode is faster with PIPE = 1 as well.
+template <int SWISH, int PIPE>
+__global__ void __launch_bounds__(256, PIPE ? 4 : 6) gn_apply_kernel(const __half* __restrict__ x,
+                                                                     const float2* __restrict__ ab,
+                                                                     __half* __restrict__ y, int HW, int C) {
   const int cv = C >> 3;                       // 8-channel vectors per pixel (16, 32 or 64)
   const int c8 = threadIdx.x % cv;
   const int prow = threadIdx.x / cv;           // pixel lane within the block
@@ -448,25 +456,50 @@ __global__ void __launch_bounds__(256, 6) gn_apply_kernel(const __half* __restri
       const float2 f = __half22float2(h2[j]);
       float v0 = fmaf(a[2 * j], f.x, b[2 * j]), v1 = fmaf(a[2 * j + 1], f.y, b[2 * j + 1]);
       if (SWISH) {
-        // two sigmoids from ONE reciprocal: 1/d0 = d1 * rcp(d0 d1).  The kernel sits at the MUFU limit (2 per element
-        // would be 116 ms of a step against 122 ms of HBM time); this makes it 1.5.  If d0 d1 overflows, rcp gives 0
-        // and both outputs are 0: the true values are then below fp16's smallest subnormal anyway.
-        const float d0 = 1.0f + __expf(-v0), d1 = 1.0f + __expf(-v1);
-        const float r = __frcp_rn(d0 * d1);
-        v0 *= r * d1;
-        v1 *= r * d0;
+        v0 = swish_fast(v0);
+        v1 = swish_fast(v1);
       }
       o2[j] = __floats2half2_rn(v0, v1);
     }
     return o;
   };
+  // software pipeline: the loads of the next batch of three pixels are in flight while this batch is normalised and
+  // stored, so the thread always has 3-6 x 16 B outstanding (without it the loads were in flight about half the time
+  // and the kernel sat at 4.1 TB/s)
   int p = blockIdx.x * ppb + prow;
-  for (; p + 2 * step < HW; p += 3 * step) {
-    uint4 u[3];
+  if constexpr (!PIPE) {
+    for (; p + 2 * step < HW; p += 3 * step) {
+      uint4 u[3];
+#pragma unroll
+      for (int i = 0; i < 3; ++i) u[i] = __ldcs(xin + (long long)(p + i * step) * cv);
+#pragma unroll
+      for (int i = 0; i < 3; ++i) yout[(long long)(p + i * step) * cv] = apply(u[i]);
+    }
+    for (; p < HW; p += step) yout[(long long)p * cv] = apply(__ldcs(xin + (long long)p * cv));
+    return;
+  }
+  uint4 u[3];
+  bool have = p + 2 * step < HW;
+  if (have) {
 #pragma unroll
     for (int i = 0; i < 3; ++i) u[i] = __ldcs(xin + (long long)(p + i * step) * cv);
+  }
+  while (have) {
+    const int pn = p + 3 * step;
+    const bool more = pn + 2 * step < HW;
+    uint4 nx[3];
+    if (more) {
+#pragma unroll
+      for (int i = 0; i < 3; ++i) nx[i] = __ldcs(xin + (long long)(pn + i * step) * cv);
+    }
 #pragma unroll
     for (int i = 0; i < 3; ++i) yout[(long long)(p + i * step) * cv] = apply(u[i]);
+    if (more) {
+#pragma unroll
+      for (int i = 0; i < 3; ++i) u[i] = nx[i];
+    }
+    p = pn;
+    have = more;
   }
   for (; p < HW; p += step) yout[(long long)p * cv] = apply(__ldcs(xin + (long long)p * cv));
 }
@@ -475,15 +508,22 @@ cudaError_t launch_gn_apply(const __half* x, const float2* ab, __half* y, int n,
                             cudaStream_t s) {
   if (C % 8 != 0 || 256 % (C / 8) != 0) return cudaErrorInvalidValue;
   const long long total_vec = (long long)n * HW * (C / 8);
-  ProfScope prof("gn_apply", 0, 0, (double)total_vec * 32.0, s);
+  char pname[48];
+  snprintf(pname, sizeof pname, "gn_apply HW%d C%d", HW, C);
+  ProfScope prof(pname, 0, 0, (double)total_vec * 32.0, s);
   const int ppb = 256 / (C / 8);
   // enough blocks to fill the machine (~16 per SM) without making the per-thread loops shorter than one batch of 4
   int chunks = (HW + ppb * 4 - 1) / (ppb * 4);
   const int want = (148 * 16 + n - 1) / n;
   if (chunks > want) chunks = want;
   if (chunks < 1) chunks = 1;
-  if (swish) gn_apply_kernel<1><<<dim3(chunks, n), 256, 0, s>>>(x, ab, y, HW, C);
-  else gn_apply_kernel<0><<<dim3(chunks, n), 256, 0, s>>>(x, ab, y, HW, C);
+  static const int pipe = [] {
+    const char* e = getenv("RGM_GN_PIPE");  // 1 (default): software-pipelined loads, 64 registers, 4 blocks per SM;
+    return e ? atoi(e) : 1;                 // 0: 40 registers, 6 blocks per SM (4.7 vs 4.9 TB/s at 128x128x128)
+  }();
+  if (swish && pipe) gn_apply_kernel<1, 1><<<dim3(chunks, n), 256, 0, s>>>(x, ab, y, HW, C);
+  else if (swish) gn_apply_kernel<1, 0><<<dim3(chunks, n), 256, 0, s>>>(x, ab, y, HW, C);
+  else gn_apply_kernel<0, 0><<<dim3(chunks, n), 256, 0, s>>>(x, ab, y, HW, C);
   return done();
 }
 
@@ -579,10 +619,8 @@ __global__ void __launch_bounds__(512) vae_out_kernel(const __half* __restrict__
         for (int j = 0; j < 4; ++j) {
           const float2 f = __half22float2(h2[j]);
           float v0 = fmaf(ga[2 * j], f.x, gb[2 * j]), v1 = fmaf(ga[2 * j + 1], f.y, gb[2 * j + 1]);
-          const float d0 = 1.0f + __expf(-v0), d1 = 1.0f + __expf(-v1);  // one reciprocal for two sigmoids, as in
-          const float r = __frcp_rn(d0 * d1);                             // gn_apply_kernel
-          v0 *= r * d1;
-          v1 *= r * d0;
+          v0 = swish_fast(v0);  // the same function and rounding as gn_apply_kernel
+          v1 = swish_fast(v1);
           o2[j] = __floats2half2_rn(v0, v1);  // the same fp16 rounding the stand-alone GroupNorm pass applies
         }
       }

@@ -249,15 +249,28 @@ __device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
 // ----------------------------------------------------------------------------------------------
 // small math helpers shared by epilogues and elementwise kernels
 // ----------------------------------------------------------------------------------------------
-// x * sigmoid(x) with MUFU ex2 + MUFU rcp (the IEEE division costs ~10 issue slots per element in the epilogues).
-// __fdividef returns 0 for a denominator above 2^126, which is the correct limit (x -> -inf gives -0).
-__device__ __forceinline__ float silu_f(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
-// GELU, tanh approximation (torch.nn.GELU(approximate="tanh")): 0.5 x (1 + tanh u) == x * sigmoid(2 u) exactly;
-// the sigmoid form needs two MUFU ops instead of tanhf's ~25 instructions (the fc1 epilogue was bound by it).
+// MUFU ex2 / rcp without the range fix-ups nvcc wraps around __expf / __fdividef / division when -ftz is not set:
+// every instruction in an epilogue or an elementwise pass is an issue slot (the GroupNorm pass was ISSUE-bound with the
+// IEEE forms: 161 instructions per 8 elements, 71 % issue-active at 55 % DRAM throughput).
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// x * sigmoid(x) = x / (1 + 2^(-x log2 e)).  x -> -inf: ex2 -> inf, rcp -> 0, result -0 (the correct limit).
+__device__ __forceinline__ float silu_f(float x) { return x * rcp_approx(1.0f + ex2_approx(x * -1.4426950408889634f)); }
+// GELU, tanh approximation (torch.nn.GELU(approximate="tanh")): 0.5 x (1 + tanh u) == x * sigmoid(2 u) exactly,
+// u = sqrt(2/pi) (x + 0.044715 x^3); the sigmoid form needs two MUFU ops instead of tanhf's ~25 instructions.
 __device__ __forceinline__ float gelu_tanh_f(float x) {
-  const float k0 = 2.0f * 0.7978845608028654f, k1 = 0.044715f;
-  const float u2 = k0 * fmaf(k1 * x * x, x, x);
-  return __fdividef(x, 1.0f + __expf(-u2));
+  constexpr float c0 = -2.0f * 0.7978845608028654f * 1.4426950408889634f;  // -2 sqrt(2/pi) log2(e)
+  constexpr float c1 = c0 * 0.044715f;
+  const float t = x * fmaf(x * x, c1, c0);                                 // -2 u log2(e)
+  return x * rcp_approx(1.0f + ex2_approx(t));
 }
 
 }  // namespace rgm

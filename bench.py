@@ -240,6 +240,7 @@ def run_b200(args):
     ms_e2e = e2.elapsed_time(e3)
     # ---- per-kernel device times for the roofline (separate pass, events around every launch) ----------------------
     vae.set_lanes(1)  # serial execution so that each launch's event pair times that launch alone
+    model.set_lanes(1)
     diffusion.enable_cuda_graphs(False)  # the per-launch event pairs are host-side calls: eager
     _lib.prof_enable(True)
     for _ in range(args.prof_steps):

@@ -45,6 +45,9 @@ typedef struct rgm_dit rgm_dit;
  * model has no label embedder; latent_w = input_size[1] (16); mlp_hidden = int(hidden * mlp_ratio) */
 int rgm_dit_create(rgm_dit** out, int depth, int hidden, int heads, int patch, int in_channels, int out_channels,
                    int label_rows, int latent_w, int mlp_hidden);
+/* 2 (default) = consecutive sample chunks alternate between two workspaces / streams so one chunk's attention and
+ * LayerNorm passes overlap the other's GEMMs; 1 = serial (per-launch profiling). */
+int rgm_dit_set_lanes(rgm_dit* h, int lanes);
 int rgm_dit_destroy(rgm_dit* h);
 /* model.load_state_dict(sd, strict=False) (scripts/sample_rule.py:71-73), one tensor per call: `key` is the reference
  * state-dict key, `src` the fp32 tensor on the device.  Returns 0 = stored (converted to the kernel layout),

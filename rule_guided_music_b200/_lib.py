@@ -42,6 +42,7 @@ _SIGNATURES = {
     "rgm_prof_summary": [c_char_p, c_int],
     "rgm_dit_create": [_HP, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int],
     "rgm_dit_destroy": [c_void_p],
+    "rgm_dit_set_lanes": [c_void_p, c_int],
     "rgm_dit_load": [c_void_p, c_char_p, c_void_p, c_ll, c_void_p],
     "rgm_dit_forward": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p],
     "rgm_vae_create": [_HP, c_int, ctypes.POINTER(c_int), c_int, c_int, c_int, c_int],

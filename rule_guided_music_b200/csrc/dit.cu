@@ -82,13 +82,24 @@ struct Dit {
   float2* rope_cs = nullptr;
   int rope_T = 0;
   bool rope_dirty = true;
-  Workspace ws;
+  // Two chunk pipelines ("lanes", like the VAE decoder's): consecutive sample chunks alternate between two workspaces
+  // and two streams, so one chunk's latency- and HBM-bound kernels (attention, LayerNorm, the residual epilogues) run
+  // while the other chunk's GEMMs hold the tensor pipe.
+  Workspace ws[2];
+  cudaStream_t lane_stream[2] = {nullptr, nullptr};
+  cudaEvent_t fork = nullptr, lane_done[2] = {nullptr, nullptr};
+  int n_lanes = 2;
   int chunk = 256;
 
   ~Dit() {
     if (w16_arena) cudaFree(w16_arena);
     if (f32_arena) cudaFree(f32_arena);
     if (rope_cs) cudaFree(rope_cs);
+    for (int l = 0; l < 2; ++l) {
+      if (lane_stream[l]) cudaStreamDestroy(lane_stream[l]);
+      if (lane_done[l]) cudaEventDestroy(lane_done[l]);
+    }
+    if (fork) cudaEventDestroy(fork);
   }
 };
 
@@ -230,12 +241,12 @@ static GemmDesc linear_desc(const __half* A, long long M, long long a_rows, int 
   return d;
 }
 
-static int dit_forward_chunk(Dit* m, const float* x, const float* t, const long long* y, float* out, int B, int H,
-                             cudaStream_t st) {
+static int dit_forward_chunk(Dit* m, void* workspace, const float* x, const float* t, const long long* y, float* out,
+                             int B, int H, cudaStream_t st) {
   const int D = m->D, T = H * m->tpt;
   const long long M = (long long)B * T;
   const long long Mp = round_up(M, 256), Bp = round_up(B, 256);
-  Carver c(m->ws.ptr);
+  Carver c(workspace);
   __half* tok16 = c.take<__half>(Mp * m->K0);
   __half* h0_16 = c.take<__half>(Mp * 256);
   float* x32 = c.take<float>(Mp * D);
@@ -408,11 +419,18 @@ int rgm_dit_create(rgm_dit** out, int depth, int hidden, int heads, int patch, i
   m->W = latent_w;
   m->mlp = mlp_hidden;
   if (const char* e = getenv("RGM_DIT_CHUNK")) m->chunk = atoi(e) > 0 ? atoi(e) : m->chunk;
+  if (const char* e = getenv("RGM_DIT_LANES")) m->n_lanes = atoi(e) >= 2 ? 2 : 1;
   if (dit_alloc(m) != 0) {
     delete m;
     return -1;
   }
   *out = reinterpret_cast<rgm_dit*>(m);
+  return 0;
+}
+
+int rgm_dit_set_lanes(rgm_dit* h, int lanes) {
+  if (!h) return set_error("rgm_dit_set_lanes: null handle");
+  reinterpret_cast<Dit*>(h)->n_lanes = lanes >= 2 ? 2 : 1;
   return 0;
 }
 
@@ -471,12 +489,39 @@ int rgm_dit_forward(rgm_dit* h, const float* x, const float* t, const long long*
     m->rope_dirty = false;
   }
   const int chunk = m->chunk < B ? m->chunk : B;
-  RGM_CUDA_OK(m->ws.reserve(dit_workspace_bytes(m, chunk, T)));
+  const int n_chunks = (B + chunk - 1) / chunk;
+  const int lanes = (m->n_lanes > 1 && n_chunks > 1) ? 2 : 1;
+  for (int l = 0; l < lanes; ++l) RGM_CUDA_OK(m->ws[l].reserve(dit_workspace_bytes(m, chunk, T)));
   const long long per_in = (long long)m->C * H * m->W, per_out = (long long)m->Cout * H * m->W;
-  for (int b0 = 0; b0 < B; b0 += chunk) {
+  if (lanes == 1) {
+    for (int b0 = 0; b0 < B; b0 += chunk) {
+      const int nb = (B - b0) < chunk ? (B - b0) : chunk;
+      if (dit_forward_chunk(m, m->ws[0].ptr, x + b0 * per_in, t + b0, y ? y + b0 : nullptr, out + b0 * per_out, nb, H,
+                            st) != 0)
+        return -1;
+    }
+    return 0;
+  }
+  // fork: both lane streams start after everything already enqueued on the caller's stream (inputs, rope table) ...
+  if (!m->fork) RGM_CUDA_OK(cudaEventCreateWithFlags(&m->fork, cudaEventDisableTiming));
+  for (int l = 0; l < 2; ++l) {
+    if (!m->lane_stream[l]) RGM_CUDA_OK(cudaStreamCreateWithFlags(&m->lane_stream[l], cudaStreamNonBlocking));
+    if (!m->lane_done[l]) RGM_CUDA_OK(cudaEventCreateWithFlags(&m->lane_done[l], cudaEventDisableTiming));
+  }
+  RGM_CUDA_OK(cudaEventRecord(m->fork, st));
+  for (int l = 0; l < 2; ++l) RGM_CUDA_OK(cudaStreamWaitEvent(m->lane_stream[l], m->fork, 0));
+  int ci = 0;
+  for (int b0 = 0; b0 < B; b0 += chunk, ++ci) {
     const int nb = (B - b0) < chunk ? (B - b0) : chunk;
-    if (dit_forward_chunk(m, x + b0 * per_in, t + b0, y ? y + b0 : nullptr, out + b0 * per_out, nb, H, st) != 0)
+    const int l = ci & 1;
+    if (dit_forward_chunk(m, m->ws[l].ptr, x + b0 * per_in, t + b0, y ? y + b0 : nullptr, out + b0 * per_out, nb, H,
+                          m->lane_stream[l]) != 0)
       return -1;
+  }
+  // ... and join: the caller's stream continues after both lanes
+  for (int l = 0; l < 2; ++l) {
+    RGM_CUDA_OK(cudaEventRecord(m->lane_done[l], m->lane_stream[l]));
+    RGM_CUDA_OK(cudaStreamWaitEvent(st, m->lane_done[l], 0));
   }
   return 0;
 }

@@ -129,6 +129,10 @@ class DiTRotary:
             torch.cuda.current_stream().synchronize()  # the staging tensors above die with this scope
         return unexpected
 
+    def set_lanes(self, lanes):
+        """2 = overlap one sample chunk's attention / LayerNorm passes with the next chunk's GEMMs (default), 1 = serial."""
+        _lib.call("rgm_dit_set_lanes", self._h, int(lanes))
+
     def _destroy(self):
         if self._h is not None:
             _lib.lib().rgm_dit_destroy(self._h)

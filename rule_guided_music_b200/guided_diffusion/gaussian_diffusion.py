@@ -502,8 +502,10 @@ class GaussianDiffusion:
                t0 > self.t_end, self.t_end, tuple((k, self._sig(v)) for k, v in kw.items() if k != "guidance_kwargs"))
         ent = self._graphs.get(key)
         if ent is None:
-            # first occurrence: eager (also grows the library's workspaces, which a capture must not do)
-            self._graphs[key] = False
+            # first occurrence: eager (also grows the library's workspaces, which a capture must not do).  A caller
+            # that hands in freshly allocated tensors every step never repeats a signature: stop remembering after 64.
+            if len(self._graphs) < 64:
+                self._graphs[key] = False
             return eager(model, x, t, t0, **kw)
         if ent is False:
             ent = _StepGraph()

@@ -75,13 +75,14 @@ attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
   // (the softmax warps wait on bar_s[1] first), so 227 KB of shared memory hold Q0, K, V^T and P.
   uint8_t* sQ1 = sP;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sP + (T / 64) * 16384u);
-  uint64_t* bar_load = bars;        // Q tiles + K + V landed
+  uint64_t* bar_load = bars;        // group A landed: Q tile 0 + K (prefetched for the next pair as soon as S is done)
+  uint64_t* bar_load_b = bars + 9;  // group B landed: Q tile 1 (staged in the P buffer) + V^T
   uint64_t* bar_s = bars + 1;       // [2] S tile complete
   uint64_t* bar_p = bars + 3;       // [2] P tile written (128 arrivals)
   uint64_t* bar_o = bars + 5;       // [2] O tile complete
   uint64_t* bar_done = bars + 7;    // epilogue has drained TMEM (128 arrivals)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
-  float* red = reinterpret_cast<float*>(bars + 10);  // [column half][row]: partner exchange of row max, then row sum
+  float* red = reinterpret_cast<float*>(bars + 12);  // [column half][row]: partner exchange of row max, then row sum
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
@@ -89,6 +90,7 @@ attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
     tma_prefetch_desc(&map_k);
     tma_prefetch_desc(&map_v);
     mbar_init(bar_load, 1);
+    mbar_init(bar_load_b, 1);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&bar_s[i], 1);
       mbar_init(&bar_p[i], 32 * ATT_SOFTMAX_WARPS);
@@ -108,36 +110,64 @@ attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
 
   const uint32_t idesc_s = umma_idesc_f16(128, T);
   const uint32_t idesc_o = umma_idesc_f16(128, p.npv);
-  const uint32_t load_bytes = p.n_tiles * q_bytes + p.nkb * k_blk + (T / 64) * v_blk;
+  const uint32_t bytes_a = q_bytes + p.nkb * k_blk;
+  const uint32_t bytes_b = (p.n_tiles - 1) * q_bytes + (T / 64) * v_blk;
+  // Operand loads of a pair arrive at HBM speed (170 KB per pair at 16 x 72: ~6 K cycles per SM when all SMs load at
+  // once), so they are issued ahead: Q0 + K of the NEXT pair as soon as this pair's S MMAs have read them, Q1 + V^T as
+  // soon as this pair's P V MMAs are done with the P buffer and V^T.
+  auto issue_a = [&](int pr) {
+    mbar_arrive_expect_tx(bar_load, bytes_a);
+    const int row0 = pr * T;
+    for (int kb = 0; kb < p.nkb; ++kb) {
+      tma_load_2d(sQ + kb * 16384, &map_q, bar_load, kb * 64, row0);
+      for (int j = 0; j < p.n_tiles; ++j)
+        tma_load_2d(sK + kb * k_blk + j * 16384, &map_k, bar_load, kb * 64, row0 + j * 128);
+    }
+  };
+  auto issue_b = [&](int pr) {
+    mbar_arrive_expect_tx(bar_load_b, bytes_b);
+    const int row0 = pr * T;
+    if (p.n_tiles > 1)
+      for (int kb = 0; kb < p.nkb; ++kb) tma_load_2d(sQ1 + kb * 16384, &map_q, bar_load_b, kb * 64, row0 + 128);
+    for (int tb = 0; tb < T / 64; ++tb) tma_load_2d(sV + tb * v_blk, &map_v, bar_load_b, tb * 64, pr * p.dh);
+  };
+  if (warp == 0 && lane == 0 && (int)blockIdx.x < p.n_pairs) {
+    issue_a(blockIdx.x);
+    issue_b(blockIdx.x);
+  }
 
   uint32_t it = 0;
   for (int pair = blockIdx.x; pair < p.n_pairs; pair += gridDim.x, ++it) {
     const uint32_t ph = it & 1;
     if (warp == 0) {
       if (lane == 0) {
-        // all MMAs of the previous pair have completed (bar_o was waited on by the epilogue, which then arrived on
-        // bar_done), so every smem operand buffer and the TMEM columns are free
+        // the epilogue of the previous pair has drained TMEM (bar_done): the S / O columns are free
+        const int next = pair + gridDim.x;
         if (it > 0) mbar_wait(bar_done, ph ^ 1);
         tc_fence_after();
-        mbar_arrive_expect_tx(bar_load, load_bytes);
-        const int row0 = pair * T;
-        for (int kb = 0; kb < p.nkb; ++kb) {
-          for (int m = 0; m < p.n_tiles; ++m)
-            tma_load_2d((m ? sQ1 : sQ) + kb * 16384, &map_q, bar_load, kb * 64, row0 + m * 128);
-          for (int j = 0; j < p.n_tiles; ++j)
-            tma_load_2d(sK + kb * k_blk + j * 16384, &map_k, bar_load, kb * 64, row0 + j * 128);
-        }
-        for (int tb = 0; tb < T / 64; ++tb) tma_load_2d(sV + tb * v_blk, &map_v, bar_load, tb * 64, pair * p.dh);
         mbar_wait(bar_load, ph);
         tc_fence_after();
-        // S tiles
+        // S tiles (tile 1 needs Q1 from group B)
         for (int m = 0; m < p.n_tiles; ++m) {
+          if (m == 1) {
+            mbar_wait(bar_load_b, ph);
+            tc_fence_after();
+          }
           for (int ks = 0; ks < p.ksteps; ++ks) {
             const int kb = ks >> 2, kk = ks & 3;
             umma_f16(tmem_base + m * 256, umma_desc_sw128((m ? sQ1 : sQ) + kb * 16384) + 2 * kk,
                      umma_desc_sw128(sK + kb * k_blk) + 2 * kk, idesc_s, ks != 0);
           }
           umma_commit(&bar_s[m]);
+        }
+        // Q0 and K have been read once the last S tile is complete: prefetch the next pair's
+        if (next < p.n_pairs) {
+          mbar_wait(&bar_s[p.n_tiles - 1], ph);
+          issue_a(next);
+        }
+        if (p.n_tiles == 1) {  // V^T (group B) has not been waited for yet
+          mbar_wait(bar_load_b, ph);
+          tc_fence_after();
         }
         // O tiles: P (A operand, K = tokens) x V^T (B operand, [npv rows][tokens])
         for (int m = 0; m < p.n_tiles; ++m) {
@@ -149,6 +179,11 @@ attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
                      umma_desc_sw128(sV + tb * v_blk) + 2 * kk, idesc_o, ks != 0);
           }
           umma_commit(&bar_o[m]);
+        }
+        // the P buffer (where Q1 is staged) and V^T are free once the last P V tile is complete
+        if (next < p.n_pairs) {
+          mbar_wait(&bar_o[p.n_tiles - 1], ph);
+          issue_b(next);
         }
       }
       __syncwarp();
@@ -305,7 +340,7 @@ cudaError_t launch_attention(const __half* q, const __half* k, const __half* vt,
       !map2d(&mv, vt, T, (unsigned long long)B * heads * dh, 64, p.npv))
     return fail("attention: cuTensorMapEncodeTiled failed");
   const size_t smem = 1024 + p.nkb * 16384 + (size_t)p.nkb * T * 128 + (size_t)(T / 64) * p.npv * 128 +
-                      (size_t)(T / 64) * 16384 + 128 + 2 * 128 * sizeof(float);
+                      (size_t)(T / 64) * 16384 + 128 + 2 * 128 * sizeof(float);  // (barriers + slots: 96 B of the 128)
   static size_t smem_set = 0;
   if (smem > smem_set) {
     cudaError_t e = cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -13,13 +13,16 @@ import torch
 import torch.distributed as dist
 
 
-def setup_dist(device=None):
+def setup_dist(device=None, port=None):
     """Initialise the default process group from RANK / WORLD_SIZE / MASTER_ADDR / MASTER_PORT (torchrun).
-    Returns (rank, world_size).  A single process needs no group."""
+    Returns (rank, world_size).  A single process needs no group.  `port` (the reference's only argument,
+    dist_util.py:21) is used as MASTER_PORT when the launcher did not set one."""
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     if world > 1 and not dist.is_initialized():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if port is not None:
+            os.environ.setdefault("MASTER_PORT", str(port))
         if torch.cuda.is_available() and device is not None and torch.device(device).type == "cuda":
             dist.init_process_group("nccl", device_id=torch.device(device))
         else:

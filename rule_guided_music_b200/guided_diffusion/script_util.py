@@ -1,8 +1,12 @@
 """create_diffusion and the argparse helpers -- mirror of guided_diffusion/script_util.py of the reference
 (diffusion_defaults :13-26, create_diffusion :106-126, create_gaussian_diffusion :462-500, add_dict_to_argparser
 :503-513, args_to_dict :516-517, str2bool :520-531).  The UNet / classifier / super-resolution factories are not on
-the sampling path."""
+the sampling path: `create_model_and_diffusion` (the UNet factory, script_util.py:129-186) raises; `NUM_CLASSES` and
+`model_and_diffusion_defaults` (:10, :74-97) are kept because scripts/sample_rule.py imports them and feeds the
+defaults to its argument parser (:311)."""
 import argparse
+
+NUM_CLASSES = 3  # number of datasets (script_util.py:10)
 
 from . import gaussian_diffusion as gd
 from .respace import SpacedDiffusion, space_timesteps
@@ -11,6 +15,22 @@ from .respace import SpacedDiffusion, space_timesteps
 def diffusion_defaults():
     return dict(learn_sigma=False, diffusion_steps=1000, noise_schedule="linear", timestep_respacing="", use_kl=False,
                 predict_xstart=False, rescale_timesteps=False, rescale_learned_sigmas=False)
+
+
+def model_and_diffusion_defaults():
+    """Argument defaults of the sampling scripts (script_util.py:74-97): the UNet fields are parsed and ignored by the
+    DiT path, the diffusion fields are what create_diffusion takes."""
+    res = dict(image_size=128, in_channels=1, num_channels=128, num_res_blocks=2, num_heads=4, num_heads_upsample=-1,
+               num_head_channels=-1, attention_resolutions="32,16,8", channel_mult="", dropout=0.0, class_cond=False,
+               use_checkpoint=False, use_scale_shift_norm=True, resblock_updown=False, use_fp16=False,
+               use_new_attention_order=False)
+    res.update(diffusion_defaults())
+    return res
+
+
+def create_model_and_diffusion(*args, **kwargs):
+    raise NotImplementedError("create_model_and_diffusion builds the UNet denoiser, which is not on the B200 sampling "
+                              "path: use DiT_models[name](...) and create_diffusion(...) as scripts/sample_rule.py does")
 
 
 def create_diffusion(learn_sigma=False, diffusion_steps=1000, noise_schedule="linear", timestep_respacing="",

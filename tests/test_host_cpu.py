@@ -127,3 +127,47 @@ def test_registry_and_config_surface(tmp_path):
     p.write_text("guidance:\n  schedule: true\n  t_start: 750\nscg:\n  num_samples: 16\n  pitch_hist: 1.0\n")
     c = load_config(str(p))
     assert c.guidance.t_start == 750 and vars(c.scg)["num_samples"] == 16
+
+
+def test_classifier_guidance_hooks_match_autograd_by_hand():
+    """composite_nn_zt (condition_functions.py:161-167 of the reference) with tiny torch classifiers: the hooks are
+    host-side autograd around the caller's classifier; check them against gradients written out by hand."""
+    from rule_guided_music_b200.guided_diffusion import condition_functions as cf
+
+    torch.manual_seed(0)
+    x = torch.randn(3, 4, 8, 16)
+    t = torch.tensor([5, 5, 5])
+    W = torch.randn(4 * 8 * 16, 6)
+    reg = lambda z, tt: z.reshape(z.shape[0], -1) @ W + tt.float().view(-1, 1)   # "regression" classifier
+    target = torch.randn(3, 6)
+    g = cf.grad_nn_zt_mse(x, t, rule=target, classifier_scale=2.0, classifier=reg)
+    pred = x.reshape(3, -1) @ W + t.float().view(-1, 1)
+    want = (-2.0 * (pred - target) @ W.t()).reshape(x.shape) * 2.0
+    torch.testing.assert_close(g, want, rtol=1e-4, atol=1e-4)
+    cls = lambda z, tt: z.reshape(z.shape[0], -1) @ W                            # class logits, queried at t = 0
+    labels = torch.tensor([[1], [4], [0]])
+    g2 = cf.grad_nn_zt_xentropy(x, rule=labels, classifier=cls)
+    logits = x.reshape(3, -1) @ W
+    p = torch.softmax(logits, -1)
+    onehot = torch.zeros_like(p).scatter_(1, labels, 1.0)
+    torch.testing.assert_close(g2, ((onehot - p) @ W.t()).reshape(x.shape), rtol=1e-4, atol=1e-5)
+    both = cf.composite_nn_zt(x, t, rule={"a": target, "b": target}, fns=["grad_nn_zt_mse", "grad_nn_zt_mse"],
+                              classifier_scales=[2.0, 1.0], classifiers=[reg, reg], rule_names=["a", "b"])
+    torch.testing.assert_close(both, want * 1.5, rtol=1e-4, atol=1e-4)
+    import pytest
+    with pytest.raises(NotImplementedError):
+        cf.composite_rule(x, t, rule={"pitch_hist": target}, fns=["rule_x0_mse_dummy"], classifier_scales=[1.0],
+                          rule_names=["pitch_hist"])
+
+
+def test_script_util_names_used_by_sample_rule():
+    from rule_guided_music_b200.guided_diffusion import script_util as su
+
+    d = su.model_and_diffusion_defaults()
+    assert su.NUM_CLASSES == 3 and d["timestep_respacing"] == "" and d["image_size"] == 128
+    import argparse, pytest
+    p = argparse.ArgumentParser()
+    su.add_dict_to_argparser(p, d)
+    assert p.parse_args(["--diffusion_steps", "500"]).diffusion_steps == 500
+    with pytest.raises(NotImplementedError):
+        su.create_model_and_diffusion()

@@ -1,9 +1,11 @@
-"""Config loading and the final latent -> piano-roll decode -- mirror of guided_diffusion/midi_util.py:26-64.
-MIDI writing, plotting and evaluation reports are host-side I/O outside the sampling path."""
+"""Config loading, the final latent -> piano-roll decode and the per-sample rule report -- mirror of
+guided_diffusion/midi_util.py:26-64, 96-124.  MIDI writing and plotting are host-side I/O outside the sampling path."""
 from types import SimpleNamespace
 
 import torch
 import yaml
+
+from ..music_rule_guidance.rule_maps import FUNC_DICT, LOSS_DICT
 
 
 def dict_to_obj(d):
@@ -41,3 +43,29 @@ def decode_sample_for_midi(sample, embed_model=None, scale_factor=1., threshold=
     roll[roll <= threshold] = -1.
     roll = ((roll + 1) * 63.5).clamp(0, 127).to(torch.uint8)
     return roll.permute(0, 2, 3, 1).contiguous()
+
+
+@torch.no_grad()
+def eval_rule_loss(generated_samples, target_rules):
+    """Rule report of finished samples (midi_util.py:96-124; scripts/sample_rule.py:241-243): for every target rule
+    the rule program is run on the decoded rolls [B,3,128,L] in [-1,1] and compared with the target by the rule's loss.
+    Returns a pandas DataFrame with the reference's columns `<rule>.target_rule`, `<rule>.gen_rule`, `<rule>.loss`,
+    one row per sample.  The script hands in a CPU tensor; the native rule kernels run on the GPU, so the rolls follow
+    the target's device (the reference moves the target to the rolls instead)."""
+    import pandas as pd
+
+    results = {}
+    B = generated_samples.shape[0]
+    # one roll tensor for all rules: they write through their input (piano mask, -0.95 threshold), so a later rule
+    # sees what an earlier one left behind, exactly like the reference's loop
+    dev = next((t.device for t in target_rules.values() if t.is_cuda), generated_samples.device)
+    rolls = generated_samples.to(dev).float()
+    for name, target in target_rules.items():
+        tl = target.tolist()
+        results[name + ".target_rule"] = [tl] if B == 1 else tl
+        gen = FUNC_DICT[name](rolls)
+        loss = LOSS_DICT[name](gen, target.to(gen.device))
+        gl = gen.tolist()
+        results[name + ".gen_rule"] = [gl] if B == 1 else gl
+        results[name + ".loss"] = loss.reshape(-1).tolist()
+    return pd.DataFrame(results)

@@ -171,3 +171,22 @@ def test_script_util_names_used_by_sample_rule():
     assert p.parse_args(["--diffusion_steps", "500"]).diffusion_steps == 500
     with pytest.raises(NotImplementedError):
         su.create_model_and_diffusion()
+
+
+def test_eval_rule_loss_report_layout():
+    """midi_util.eval_rule_loss with a user-registered (pure-torch) rule: one row per sample, the reference's columns."""
+    from rule_guided_music_b200.guided_diffusion import midi_util
+    from rule_guided_music_b200.music_rule_guidance import rule_maps
+
+    rule_maps.FUNC_DICT["mean_velocity"] = lambda roll: roll[:, 0].mean(dim=(1, 2)).unsqueeze(-1)
+    rule_maps.LOSS_DICT["mean_velocity"] = lambda gen, tgt: ((gen - tgt) ** 2).mean(dim=-1)
+    try:
+        rolls = torch.linspace(-1, 1, 2 * 3 * 128 * 256).reshape(2, 3, 128, 256)
+        target = torch.tensor([[0.0], [0.5]])
+        df = midi_util.eval_rule_loss(rolls, {"mean_velocity": target})
+        assert list(df.columns) == ["mean_velocity.target_rule", "mean_velocity.gen_rule", "mean_velocity.loss"]
+        assert len(df) == 2
+        want = (rolls[:, 0].mean(dim=(1, 2)) - target[:, 0]) ** 2
+        torch.testing.assert_close(torch.tensor(df["mean_velocity.loss"].tolist()), want)
+    finally:
+        del rule_maps.FUNC_DICT["mean_velocity"], rule_maps.LOSS_DICT["mean_velocity"]

@@ -98,3 +98,19 @@ def test_select_first_max_with_ties(cuda, N, B, elems):
     assert torch.equal(out.cpu(), cand[ref_idx, torch.arange(B)])
     if N >= 3:
         assert torch.tensor([[0., 1], [0, 1], [-1, 1]]).argmax(0).tolist() == [0, 0]
+
+
+def test_eval_rule_loss_runs_native_rules_from_a_cpu_roll(cuda):
+    """scripts/sample_rule.py:241-243 hands eval_rule_loss a CPU roll rebuilt from the uint8 MIDI array; the native
+    rule kernels run where the targets live.  Values equal the oracle's rules + losses on the same roll."""
+    from rule_guided_music_b200.guided_diffusion import midi_util
+
+    roll = gi.rule_rolls()["random"]
+    B = roll.shape[0]
+    tp = torch.tensor([[0.5, 0, 0, 0, 0.25, 0, 0, 0.25, 0, 0, 0, 0]]).repeat(B, 1)
+    df = midi_util.eval_rule_loss(roll.clone(), {"pitch_hist": tp.to(cuda)})
+    assert len(df) == B and list(df.columns) == ["pitch_hist.target_rule", "pitch_hist.gen_rule", "pitch_hist.loss"]
+    ref_gen = orules.FUNC_DICT["pitch_hist"](roll.clone())
+    ref_loss = orules.LOSS_DICT["pitch_hist"](ref_gen, tp)
+    np.testing.assert_allclose(np.array(df["pitch_hist.gen_rule"].tolist()), ref_gen.numpy(), rtol=2e-6, atol=1e-7)
+    np.testing.assert_allclose(np.array(df["pitch_hist.loss"].tolist()), ref_loss.numpy(), rtol=1e-5, atol=1e-9)

@@ -167,6 +167,30 @@ def golden_vae_enc():
     save("vae_enc", **out)
 
 
+def golden_collage():
+    """DiffCollage workers and window split / merge of the reference (diff_collage/*.py) with an analytic denoiser."""
+    import diff_collage as dc
+    from diff_collage.w_img import avg_merge_wimg, split_wimg
+
+    out = {}
+    for n in (2, 3, 5):
+        for circle in (False, True):
+            x, t, y = gi.collage_inputs(n, circle)
+            cls = dc.CondIndCircle if circle else dc.CondIndSimple
+            worker = cls((4, 4, 128), gi.collage_eps_fn, n, overlap_size=64)
+            tag = f"n{n}_{'circle' if circle else 'long'}"
+            assert tuple(worker.shape) == (4, 4, x.shape[-1])
+            out[tag + "__eps_y"] = worker.eps_scalar_t_fn(x, t, y=y)[..., ::2].numpy()  # every other column: fixture size
+            out[tag + "__eps_noy"] = worker.eps_scalar_t_fn(x, t)[..., 1::2].numpy()
+    x, _, _ = gi.collage_inputs(4, False)
+    tiles, ov = split_wimg(x, 4)
+    out["split4"] = tiles.numpy()
+    out["split4_overlap"] = np.array(ov)
+    out["merge4_avg"] = avg_merge_wimg(tiles * 2.0, ov, n=4).numpy()
+    out["merge4_sum"] = avg_merge_wimg(tiles, ov, n=4, is_avg=False).numpy()
+    save("collage", **out)
+
+
 def golden_sampler():
     """Short guided trajectories through the reference's own loops (seeded torch CPU RNG = shared noise stream)."""
     embed = build_ref_vae()
@@ -273,6 +297,6 @@ def golden_sampler_ext():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["schedule", "rules", "dit", "vae", "vae_enc", "sampler", "sampler_ext"]
+    which = sys.argv[1:] or ["schedule", "rules", "dit", "vae", "vae_enc", "collage", "sampler", "sampler_ext"]
     for w in which:
         globals()["golden_" + w]()

@@ -205,3 +205,20 @@ def ext_model_kwargs(cfg):
     kw = {"y": torch.ones(B, dtype=torch.long)}
     kw["rule"] = rule_targets(B, cfg.get("rule_len", H * 8), cfg["rules"])
     return kw
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# DiffCollage workers on the CPU with an analytic denoiser (host logic of SURVEY.md section 8 row a12)
+# ---------------------------------------------------------------------------------------------------------------
+def collage_eps_fn(x, t, y=None):
+    """A cheap stand-in for the denoiser with the worker-side signature: any window width, per-row t and y."""
+    out = torch.sin(x * (1.0 + 0.01 * t.view(-1, 1, 1, 1).float())) + 0.05 * x.flip(-1)
+    if y is not None:
+        out = out + 0.1 * y.view(-1, 1, 1, 1).float()
+    return out
+
+
+def collage_inputs(num_img, circle, B=2):
+    g = torch.Generator(device="cpu").manual_seed(60 + num_img + (7 if circle else 0))
+    W = 128 * num_img - 64 * (num_img if circle else num_img - 1)
+    return torch.randn(B, 4, 4, W, generator=g), torch.tensor([17, 803][:B]), torch.tensor([1, 2][:B])

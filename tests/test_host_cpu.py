@@ -190,3 +190,31 @@ def test_eval_rule_loss_report_layout():
         torch.testing.assert_close(torch.tensor(df["mean_velocity.loss"].tolist()), want)
     finally:
         del rule_maps.FUNC_DICT["mean_velocity"], rule_maps.LOSS_DICT["mean_velocity"]
+
+
+def test_diff_collage_workers_match_reference_on_cpu():
+    """CondIndSimple / CondIndCircle and the window split / merge are host logic in
+    torch: with an analytic denoiser they run on the CPU and must reproduce the reference's workers
+    (tests/golden/collage.npz, made by diff_collage/*.py of the reference with the same inputs)."""
+    from rule_guided_music_b200 import diff_collage as dc
+    from rule_guided_music_b200.diff_collage.w_img import avg_merge_wimg, split_wimg
+
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "collage.npz"))
+    for n in (2, 3, 5):
+        for circle in (False, True):
+            x, t, y = gi.collage_inputs(n, circle)
+            cls = dc.CondIndCircle if circle else dc.CondIndSimple
+            worker = cls((4, 4, 128), gi.collage_eps_fn, n, overlap_size=64)
+            tag = f"n{n}_{'circle' if circle else 'long'}"
+            assert tuple(worker.shape) == (4, 4, x.shape[-1])
+            np.testing.assert_allclose(worker.eps_scalar_t_fn(x, t, y=y)[..., ::2].numpy(), gold[tag + "__eps_y"],
+                                       rtol=1e-6, atol=1e-6, err_msg=tag)
+            np.testing.assert_allclose(worker.eps_scalar_t_fn(x, t)[..., 1::2].numpy(), gold[tag + "__eps_noy"],
+                                       rtol=1e-6, atol=1e-6, err_msg=tag)
+    x, _, _ = gi.collage_inputs(4, False)
+    tiles, ov = split_wimg(x, 4)
+    assert ov == int(gold["split4_overlap"])
+    np.testing.assert_array_equal(tiles.numpy(), gold["split4"])
+    np.testing.assert_allclose(avg_merge_wimg(tiles * 2.0, ov, n=4).numpy(), gold["merge4_avg"], rtol=1e-6, atol=1e-6)
+    np.testing.assert_allclose(avg_merge_wimg(tiles, ov, n=4, is_avg=False).numpy(), gold["merge4_sum"], rtol=1e-6,
+                               atol=1e-6)

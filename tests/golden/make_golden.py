@@ -191,6 +191,27 @@ def golden_collage():
     save("collage", **out)
 
 
+def golden_host():
+    """Host-logic branches of the reference's sampler with an analytic denoiser (no networks, no SCG)."""
+    out = {}
+    for tag, cfg in gi.HOST_CASES.items():
+        d = _create_diffusion(learn_sigma=cfg.get("learn_sigma", False), diffusion_steps=1000, noise_schedule="linear",
+                              timestep_respacing=cfg["respacing"], use_kl=False, predict_xstart=False,
+                              rescale_timesteps=cfg.get("rescale", False), rescale_learned_sigmas=False)
+        fn = partial(gi.host_model, learn_sigma=cfg.get("learn_sigma", False))
+        guidance = SimpleNamespace(**cfg["guidance"]) if cfg.get("guidance") else None
+        loop = d.ddim_sample_loop_progressive if cfg["ddim"] else d.p_sample_loop_progressive
+        extra = {"eta": cfg["eta"]} if cfg["ddim"] else {}
+        torch.manual_seed(cfg["seed"])
+        d.t_end = cfg.get("t_end", 0)
+        steps = [o["sample"].numpy().copy() for o in loop(
+            fn, gi.HOST_SHAPE, model_kwargs={"y": torch.tensor([1, 2])}, device="cpu", t_end=cfg.get("t_end", 0),
+            clip_denoised=cfg.get("clip", True), cond_fn=gi.analytic_cond_fn if cfg.get("cond") else None,
+            guidance_kwargs=guidance, edit_kwargs=gi.host_edit_inputs() if cfg.get("edit") else None, **extra)]
+        out[tag] = np.stack(steps)
+    save("host", **out)
+
+
 def golden_sampler():
     """Short guided trajectories through the reference's own loops (seeded torch CPU RNG = shared noise stream)."""
     embed = build_ref_vae()
@@ -297,6 +318,6 @@ def golden_sampler_ext():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["schedule", "rules", "dit", "vae", "vae_enc", "collage", "sampler", "sampler_ext"]
+    which = sys.argv[1:] or ["schedule", "rules", "dit", "vae", "vae_enc", "collage", "host", "sampler", "sampler_ext"]
     for w in which:
         globals()["golden_" + w]()

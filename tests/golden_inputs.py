@@ -222,3 +222,43 @@ def collage_inputs(num_img, circle, B=2):
     g = torch.Generator(device="cpu").manual_seed(60 + num_img + (7 if circle else 0))
     W = 128 * num_img - 64 * (num_img if circle else num_img - 1)
     return torch.randn(B, 4, 4, W, generator=g), torch.tensor([17, 803][:B]), torch.tensor([1, 2][:B])
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# host-logic branches of the sampler on the CPU with an analytic denoiser: classifier
+# guidance with and without a schedule, DDIM score conditioning, replacement editing, learned-range variances,
+# rescaled timesteps, t_end.  No SCG here (its fan-out / decode / select are kernels, covered by the GPU tests).
+# ---------------------------------------------------------------------------------------------------------------
+def host_model(x, t, y=None, rule=None, learn_sigma=False):
+    tt = t.float().view(-1, 1, 1, 1)
+    eps = torch.tanh(x) * 0.5 + 0.0007 * tt + 0.02 * x.roll(1, dims=2)
+    if y is not None:
+        eps = eps + 0.05 * y.float().view(-1, 1, 1, 1)
+    if learn_sigma:
+        return torch.cat([eps, torch.sin(x + 0.001 * tt)], dim=1)   # second half: variance interpolation in [-1, 1]
+    return eps
+
+
+def host_edit_inputs():
+    g = torch.Generator(device="cpu").manual_seed(71)
+    gt = torch.randn(2, 4, 32, 16, generator=g) * 0.6
+    mask = torch.zeros(2, 1, 32, 1)
+    mask[:, :, :16] = 1.0
+    return {"gt": gt, "mask": mask, "noise_level": 4, "l_start": 16, "l_end": 32}
+
+
+_SCHED = dict(schedule=True, t_start=800, t_end=100, interval=2, method="classifier", step_size=1.0, nn=False)
+_ALWAYS = dict(schedule=False, t_start=750, t_end=0, interval=1, method="classifier", step_size=1.0, nn=False)
+HOST_CASES = {
+    "ddpm_cond_sched": dict(respacing="6", ddim=False, seed=81, guidance=_SCHED, cond=True),
+    "ddim_cond_score": dict(respacing="5", ddim=True, eta=0.0, seed=82, guidance=_ALWAYS, cond=True),
+    "ddim_eta1_tend": dict(respacing="6", ddim=True, eta=1.0, seed=83, t_end=2),
+    # (replacement editing together with a classifier-gradient cond_fn raises a shape error in the reference itself,
+    # gaussian_diffusion.py:409-413 multiplies the full-length variance with the cropped gradient: not a golden case)
+    "ddpm_edit": dict(respacing="6", ddim=False, seed=84, edit=True),
+    "ddim_edit": dict(respacing="6", ddim=True, eta=0.5, seed=88, edit=True),
+    "ddpm_learn_sigma": dict(respacing="5", ddim=False, seed=85, learn_sigma=True),
+    "ddpm_rescaled_t": dict(respacing="ddim4", ddim=False, seed=86, rescale=True),
+    "ddpm_no_clip": dict(respacing="4", ddim=False, seed=87, clip=False),
+}
+HOST_SHAPE = (2, 4, 32, 16)

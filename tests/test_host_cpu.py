@@ -218,3 +218,32 @@ def test_diff_collage_workers_match_reference_on_cpu():
     np.testing.assert_allclose(avg_merge_wimg(tiles * 2.0, ov, n=4).numpy(), gold["merge4_avg"], rtol=1e-6, atol=1e-6)
     np.testing.assert_allclose(avg_merge_wimg(tiles, ov, n=4, is_avg=False).numpy(), gold["merge4_sum"], rtol=1e-6,
                                atol=1e-6)
+
+
+@pytest.mark.parametrize("tag", list(gi.HOST_CASES))
+def test_sampler_host_branches_match_reference_on_cpu(tag):
+    """Classifier guidance (with / without schedule), DDIM score conditioning, replacement editing, learned-range
+    variance, rescaled timesteps, t_end, clip off: host logic of rows a4-a6, run on the CPU with an analytic denoiser
+    against trajectories of the unmodified reference (tests/golden/host.npz)."""
+    from types import SimpleNamespace
+
+    from rule_guided_music_b200.guided_diffusion.script_util import create_diffusion as full_create
+
+    g = np.load(os.path.join(GOLD, "host.npz"))
+    cfg = gi.HOST_CASES[tag]
+    d = full_create(learn_sigma=cfg.get("learn_sigma", False), diffusion_steps=1000, noise_schedule="linear",
+                    timestep_respacing=cfg["respacing"], use_kl=False, predict_xstart=False,
+                    rescale_timesteps=cfg.get("rescale", False), rescale_learned_sigmas=False)
+    fn = partial(gi.host_model, learn_sigma=cfg.get("learn_sigma", False))
+    guidance = SimpleNamespace(**cfg["guidance"]) if cfg.get("guidance") else None
+    loop = d.ddim_sample_loop_progressive if cfg["ddim"] else d.p_sample_loop_progressive
+    extra = {"eta": cfg["eta"]} if cfg["ddim"] else {}
+    torch.manual_seed(cfg["seed"])
+    d.t_end = cfg.get("t_end", 0)
+    steps = [o["sample"].numpy().copy() for o in loop(
+        fn, gi.HOST_SHAPE, model_kwargs={"y": torch.tensor([1, 2])}, device="cpu", t_end=cfg.get("t_end", 0),
+        clip_denoised=cfg.get("clip", True), cond_fn=gi.analytic_cond_fn if cfg.get("cond") else None,
+        guidance_kwargs=guidance, edit_kwargs=gi.host_edit_inputs() if cfg.get("edit") else None, **extra)]
+    ref = g[tag]
+    assert len(steps) == ref.shape[0]
+    np.testing.assert_allclose(np.stack(steps), ref, atol=2e-5, rtol=1e-4)

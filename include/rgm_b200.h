@@ -11,7 +11,8 @@
  * Conventions
  *   - plain pointers and sizes only; all pointers are DEVICE pointers unless the name ends in _host
  *   - all work is enqueued on the caller's stream (a cudaStream_t passed as void*); compute calls do not synchronise
- *     (a handle's workspace grows on first use of a larger batch, which does synchronise once)
+ *     (a handle's workspace grows on first use of a larger batch: one cudaMalloc, nothing is freed until *_destroy;
+ *     rgm_*_reserve pre-sizes)
  *   - return 0 on success, negative on error; rgm_last_error() returns the message for the calling thread
  *   - handles own their packed weights and workspace; one handle is used by one host thread at a time
  *   - there is no CPU fallback: without an sm_100 device every compute entry point fails with an error
@@ -49,6 +50,11 @@ int rgm_dit_create(rgm_dit** out, int depth, int hidden, int heads, int patch, i
  * LayerNorm passes overlap the other's GEMMs; 1 = serial (per-launch profiling). */
 int rgm_dit_set_lanes(rgm_dit* h, int lanes);
 int rgm_dit_destroy(rgm_dit* h);
+/* Pre-size the handle's workspaces and rotary table for batches of up to B samples of latent height H (what the first
+ * rgm_dit_forward of that size would allocate).  Buffers only grow and a grown buffer's predecessor stays allocated
+ * until rgm_dit_destroy, so a CUDA graph captured earlier keeps replaying into valid memory; growth while the caller's
+ * stream is being captured is refused with an error instead -- reserve (or run the shape once eagerly) before capture. */
+int rgm_dit_reserve(rgm_dit* h, int B, int H);
 /* model.load_state_dict(sd, strict=False) (scripts/sample_rule.py:71-73), one tensor per call: `key` is the reference
  * state-dict key, `src` the fp32 tensor on the device.  Returns 0 = stored (converted to the kernel layout),
  * 1 = key not part of this path (ignored), negative = error (element count mismatch).
@@ -66,6 +72,9 @@ typedef struct rgm_vae rgm_vae;
 int rgm_vae_create(rgm_vae** out, int ch, const int* ch_mult_host, int n_levels, int num_res_blocks, int z_channels,
                    int out_ch);
 int rgm_vae_destroy(rgm_vae* h);
+/* Pre-size the activation buffers for decodes / encodes of up to n_tiles 16x16 latent tiles (same contract as
+ * rgm_dit_reserve). */
+int rgm_vae_reserve(rgm_vae* h, int n_tiles);
 /* 2 (default): consecutive tile chunks alternate between two internal streams so GroupNorm passes overlap convolutions;
  * 1: strictly serial on the caller's stream (used for per-kernel timing) */
 int rgm_vae_set_lanes(rgm_vae* h, int lanes);
@@ -108,6 +117,65 @@ int rgm_x0_from_eps(const float* x, const float* eps, const float* a, const floa
 /* :539-554  max_ind = total.view(N, B).argmax(0) (first maximal index); out[b] = cand[max_ind[b], b]; idx int64 [B] */
 int rgm_scg_select(const float* total, const float* cand, float* out, long long* idx, int N, int B, long long elems,
                    void* stream);
+
+/* ---- one whole SCG step from a C host --------------------------------------------------- */
+/* GaussianDiffusion.__init__ (gaussian_diffusion.py:142-186) for the (respaced) betas of SpacedDiffusion
+ * (respace.py:63-95): float64 on the host in numpy's operation order, cast to fp32 once (what _extract_into_tensor
+ * :1331-1344 does per lookup), written to out_device as RGM_COEF_ROWS rows of T floats, row r at out_device + r*T. */
+enum {
+  RGM_COEF_BETAS = 0,
+  RGM_COEF_ALPHAS_CUMPROD,
+  RGM_COEF_ALPHAS_CUMPROD_PREV,
+  RGM_COEF_SQRT_ALPHAS_CUMPROD,
+  RGM_COEF_SQRT_ONE_MINUS_ALPHAS_CUMPROD,
+  RGM_COEF_SQRT_RECIP_ALPHAS_CUMPROD,
+  RGM_COEF_SQRT_RECIPM1_ALPHAS_CUMPROD,
+  RGM_COEF_POSTERIOR_VARIANCE,
+  RGM_COEF_POSTERIOR_LOG_VARIANCE_CLIPPED,
+  RGM_COEF_POSTERIOR_MEAN_COEF1,
+  RGM_COEF_POSTERIOR_MEAN_COEF2,
+  RGM_COEF_FIXED_LARGE_VARIANCE,     /* append(posterior_variance[1], betas[1:])   (:316-329) */
+  RGM_COEF_FIXED_LARGE_LOG_VARIANCE,
+  RGM_COEF_LOG_BETAS,
+  RGM_COEF_ROWS
+};
+int rgm_coeff_tables(const double* betas_host, int T, float* out_device, void* stream);
+/* the same tables into a HOST buffer (no device needed; what the CPU-side tests pin against numpy) */
+int rgm_coeff_tables_host(const double* betas_host, int T, float* out_host);
+/* ddim_sample between the denoiser call and the noise (:921-944): pred_xstart = clip(sqrt_recip*x - sqrt_recipm1*eps),
+ * eps re-derived from it, sigma[b] = eta*sqrt((1-abar_prev)/(1-abar))*sqrt(1-abar/abar_prev),
+ * mean_pred = pred_xstart*sqrt(abar_prev) + sqrt(1-abar_prev-sigma^2)*eps.  t_index int64 [B] indexes the tables. */
+int rgm_ddim_mean(const float* x, const float* eps, const float* coeff_tables, int T, const long long* t_index,
+                  float eta, int clip_denoised, float* pred_xstart, float* mean_pred, float* sigma, int B,
+                  long long elems, void* stream);
+
+/* One rule of model_kwargs["rule"] with its scg_kwargs weight (FUNC_DICT / LOSS_DICT entries, rule_maps.py:5-38). */
+enum { RGM_RULE_PITCH_HIST = 0, RGM_RULE_NOTE_DENSITY = 1, RGM_RULE_NOTE_DENSITY_CLASS = 2 };
+typedef struct rgm_rule_spec {
+  int kind;               /* RGM_RULE_* */
+  int interval;           /* note density: window in roll columns (128; 16 for note_density_pixel) */
+  float horizontal_scale; /* note density: 5 (default), 1 / 2 for the _hr_ variants, 1 for the class variant */
+  int loss_kind;          /* 0 = mse_loss_mean, 1 = zero_one_loss_mean */
+  float weight;           /* scg_kwargs.get(rule_name, 1.) */
+  const float* target;    /* DEVICE f32 [B, K]: K = 12 (pitch_hist) or 2 * L / interval (class targets as floats) */
+} rgm_rule_spec;
+
+/* scg_sample (gaussian_diffusion.py:491-554) in one call.  The handle owns the candidate / roll scratch (grown on first
+ * use or by rgm_scg_reserve; same no-free contract as rgm_dit_reserve).  vae may be NULL (embed_model=None, :523). */
+typedef struct rgm_scg rgm_scg;
+int rgm_scg_create(rgm_scg** out, rgm_dit* dit, rgm_vae* vae);
+int rgm_scg_reserve(rgm_scg* h, int N, int B, int C, int H, int W);
+int rgm_scg_destroy(rgm_scg* h);
+/* mean f32 [B,C,H,W] (mean_pred / p_mean_var["mean"]), g f32 [B] (sigma or exp(0.5*log_variance)), noise f32
+ * [N,B,C,H,W] (th.randn_like, :512), t_model f32 [B] = the timestep the denoiser is called with (already mapped by
+ * respace.py:123-128), y int64 [B] or NULL, x0_a / x0_c f32 [B] = sqrt_recip_alphas_cumprod[t] /
+ * sqrt_recipm1_alphas_cumprod[t] (:359-364), rules_host = n_rules specs in dict order (the rule programs write through
+ * the roll, so order matters).  out_sample f32 [B,C,H,W] = the chosen x_(t-1), out_index int64 [B] = max_ind,
+ * out_scores f32 [N*B] = total_log_prob (candidate-major) or NULL. */
+int rgm_scg_step(rgm_scg* h, const float* mean, const float* g, const float* noise, const float* t_model,
+                 const long long* y, const float* x0_a, const float* x0_c, float scale_factor,
+                 const rgm_rule_spec* rules_host, int n_rules, int N, int B, int C, int H, int W, float* out_sample,
+                 long long* out_index, float* out_scores, void* stream);
 
 /* ---- building blocks (exposed for the parity tests) ---------------------------------------------------------- */
 /* out32[M,N] = A16[M,K] . B16[N,K]^T + bias[N]      (torch.nn.functional.linear; reference dit.py:256,286,324-326)

@@ -14,7 +14,7 @@ import torch.nn.functional as F
 
 def timestep_embedding(t, dim=256, max_period=10000):
     half = dim // 2
-    freqs = torch.exp(-math.log(max_period) * torch.arange(0, half, dtype=torch.float32) / half)
+    freqs = torch.exp(-math.log(max_period) * torch.arange(0, half, dtype=torch.float32) / half).to(t.device)
     args = t[:, None].float() * freqs[None]
     return torch.cat([torch.cos(args), torch.sin(args)], dim=-1)
 
@@ -22,7 +22,7 @@ def timestep_embedding(t, dim=256, max_period=10000):
 def rotate_queries_or_keys(x, freqs):
     """x [B, heads, T, hd]; freqs [rot_dim/2].  Rotates features [0, rot_dim) in interleaved pairs."""
     T = x.shape[-2]
-    ang = torch.arange(T, dtype=freqs.dtype)[:, None] * freqs[None, :]  # [T, rot/2]
+    ang = torch.arange(T, dtype=freqs.dtype, device=freqs.device)[:, None] * freqs[None, :]  # [T, rot/2]
     ang = ang.repeat_interleave(2, dim=-1)                              # [T, rot]  (f0,f0,f1,f1,...)
     rot = ang.shape[-1]
     xr, xp = x[..., :rot], x[..., rot:]

@@ -26,7 +26,7 @@ def total_pitch_class_histogram(roll):
     pr = piano_like(roll[:, :1, :, :])
     pr = ((pr + 1) / 2.0).squeeze(dim=1)
     per_pitch = pr.sum(dim=-1)                                            # [B,128]
-    padded = torch.cat((per_pitch, torch.zeros(pr.shape[0], 4)), dim=-1)  # [B,132]
+    padded = torch.cat((per_pitch, torch.zeros(pr.shape[0], 4, device=pr.device)), dim=-1)  # [B,132]
     hist = padded.reshape(-1, 11, 12).permute(0, 2, 1).sum(dim=-1)        # fold pitch mod 12
     hist = hist / (hist.sum(dim=-1, keepdim=True) + 1e-12)
     return hist.squeeze(dim=0) if hist.shape[0] == 1 else hist
@@ -55,8 +55,8 @@ def note_density(roll, interval=128, quantize_factor=1, horizontal_scale=5):
 
 
 def note_density_class(roll, interval=128, quantize_factor=1, horizontal_scale=1):
-    vt = torch.tensor(VERTICAL_ND_BOUNDS)
-    hr = torch.tensor(HORIZONTAL_ND_BOUNDS) / horizontal_scale
+    vt = torch.tensor(VERTICAL_ND_BOUNDS).to(roll.device)
+    hr = torch.tensor(HORIZONTAL_ND_BOUNDS).to(roll.device) / horizontal_scale
     nd = note_density(roll, interval=interval, quantize_factor=quantize_factor, horizontal_scale=horizontal_scale)
     n = nd.shape[-1]
     return torch.cat((torch.bucketize(nd[:, :n // 2], vt), torch.bucketize(nd[:, n // 2:], hr)), dim=-1)

@@ -20,7 +20,7 @@ from . import schedule as osched
 
 
 def _extract(arr, t, shape):
-    res = torch.from_numpy(np.asarray(arr, dtype=np.float64))[t].float()
+    res = torch.from_numpy(np.asarray(arr, dtype=np.float64)).to(t.device)[t].float()
     while res.dim() < len(shape):
         res = res[..., None]
     return res.expand(shape)
@@ -31,7 +31,7 @@ class _Wrapped:
         self.model, self.tmap, self.rescale, self.orig = model, tmap, rescale, orig_steps
 
     def __call__(self, x, ts, **kw):
-        new_ts = torch.tensor(self.tmap, dtype=ts.dtype)[ts]
+        new_ts = torch.tensor(self.tmap, dtype=ts.dtype, device=ts.device)[ts]
         if self.rescale:
             new_ts = new_ts.float() * (1000.0 / self.orig)
         return self.model(x, new_ts, **kw)
@@ -113,7 +113,7 @@ class OracleDiffusion:
         total = total.view(n, -1)
         max_ind = total.argmax(dim=0)
         sample = sample.view(n, *mean_pred.shape)
-        chosen = sample[max_ind, torch.arange(mean_pred.shape[0])]
+        chosen = sample[max_ind, torch.arange(mean_pred.shape[0], device=max_ind.device)]
         if trace is not None:
             trace.append({"candidates": sample.clone(), "eps": eps.clone(), "roll": x0.clone(),
                           "total_log_prob": total.clone(), "max_ind": max_ind.clone()})

@@ -37,11 +37,34 @@ def _declare(lib):
 # name -> argtypes; every function returns int (0 = ok)
 _HP = ctypes.POINTER(ctypes.c_void_p)
 c_char_p = ctypes.c_char_p
+class RuleSpec(ctypes.Structure):
+    """rgm_rule_spec of include/rgm_b200.h."""
+    _fields_ = [("kind", c_int), ("interval", c_int), ("horizontal_scale", c_float), ("loss_kind", c_int),
+                ("weight", c_float), ("target", c_void_p)]
+
+
+COEF_ROWS = ["betas", "alphas_cumprod", "alphas_cumprod_prev", "sqrt_alphas_cumprod", "sqrt_one_minus_alphas_cumprod",
+             "sqrt_recip_alphas_cumprod", "sqrt_recipm1_alphas_cumprod", "posterior_variance",
+             "posterior_log_variance_clipped", "posterior_mean_coef1", "posterior_mean_coef2", "fixed_large_variance",
+             "fixed_large_log_variance", "log_betas"]  # RGM_COEF_* order
+
 _SIGNATURES = {
     "rgm_prof_enable": [c_int],
     "rgm_prof_summary": [c_char_p, c_int],
     "rgm_dit_create": [_HP, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int],
     "rgm_dit_destroy": [c_void_p],
+    "rgm_dit_reserve": [c_void_p, c_int, c_int],
+    "rgm_vae_reserve": [c_void_p, c_int],
+    "rgm_coeff_tables": [ctypes.POINTER(c_double), c_int, c_void_p, c_void_p],
+    "rgm_coeff_tables_host": [ctypes.POINTER(c_double), c_int, ctypes.POINTER(c_float)],
+    "rgm_ddim_mean": [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_float, c_int, c_void_p, c_void_p, c_void_p, c_int,
+                      c_ll, c_void_p],
+    "rgm_scg_create": [_HP, c_void_p, c_void_p],
+    "rgm_scg_reserve": [c_void_p, c_int, c_int, c_int, c_int, c_int],
+    "rgm_scg_destroy": [c_void_p],
+    "rgm_scg_step": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float,
+                     ctypes.POINTER(RuleSpec), c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
+                     c_void_p],
     "rgm_dit_set_lanes": [c_void_p, c_int],
     "rgm_dit_load": [c_void_p, c_char_p, c_void_p, c_ll, c_void_p],
     "rgm_dit_forward": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p],

@@ -341,14 +341,10 @@ cudaError_t launch_attention(const __half* q, const __half* k, const __half* vt,
     return fail("attention: cuTensorMapEncodeTiled failed");
   const size_t smem = 1024 + p.nkb * 16384 + (size_t)p.nkb * T * 128 + (size_t)(T / 64) * p.npv * 128 +
                       (size_t)(T / 64) * 16384 + 128 + 2 * 128 * sizeof(float);  // (barriers + slots: 96 B of the 128)
-  static size_t smem_set = 0;
-  if (smem > smem_set) {
-    cudaError_t e = cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) {
-      if (err) *err = std::string("attention: cudaFuncSetAttribute(shared memory): ") + cudaGetErrorString(e);
-      return e;
-    }
-    smem_set = smem;
+  static SmemAttr attr;
+  if (cudaError_t e = attr.ensure(attention_kernel, smem); e != cudaSuccess) {
+    if (err) *err = std::string("attention: cudaFuncSetAttribute(shared memory): ") + cudaGetErrorString(e);
+    return e;
   }
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);

@@ -670,12 +670,8 @@ cudaError_t launch_vae_out(const __half* x, const float2* ab, const float* w, co
   if (C % 16 != 0 || 512 % (C / 8) != 0 || out_ch < 1 || out_ch > 8 || roll_ch > out_ch) return cudaErrorInvalidValue;
   const size_t smem = ((18 * 18 * (C * 2 + 16) + 15) & ~15) + (size_t)9 * (C / 16) * 32 * sizeof(uint2) +
                       (size_t)C * sizeof(float2);
-  static size_t smem_set = 0;
-  if (smem > smem_set) {
-    cudaError_t e = cudaFuncSetAttribute(vae_out_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    smem_set = smem;
-  }
+  static SmemAttr attr;
+  if (cudaError_t e = attr.ensure(vae_out_kernel, smem); e != cudaSuccess) return e;
   ProfScope prof("vae_out(norm+swish+conv_out+roll)", 2.0 * n * 16384.0 * out_ch * 9.0 * C, 2.0 * n * 16384.0 * 8 * 9.0 * C,
                  (double)n * 16384.0 * (C * 2.0 + roll_ch * 4.0), s);
   vae_out_kernel<<<dim3(64, n), 512, smem, s>>>(x, ab, w, bias, roll, C, out_ch, tile0, n_cand, roll_len, roll_ch);

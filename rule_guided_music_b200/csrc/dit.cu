@@ -33,26 +33,7 @@ __global__ void convert_pad_kernel(const float* __restrict__ src, __half* __rest
 
 static inline long long round_up(long long a, long long b) { return (a + b - 1) / b * b; }
 
-struct Workspace {
-  void* ptr = nullptr;
-  size_t bytes = 0;
-  cudaError_t reserve(size_t need) {
-    if (need <= bytes) return cudaSuccess;
-    if (ptr) {
-      cudaError_t e = cudaDeviceSynchronize();
-      if (e != cudaSuccess) return e;
-      cudaFree(ptr);
-      ptr = nullptr;
-      bytes = 0;
-    }
-    cudaError_t e = cudaMalloc(&ptr, need);
-    if (e == cudaSuccess) bytes = need;
-    return e;
-  }
-  ~Workspace() {
-    if (ptr) cudaFree(ptr);
-  }
-};
+using Workspace = GrowBuf;  // api_util.h: grows by retiring, never frees what a captured graph may reference
 
 struct Carver {
   uint8_t* base;
@@ -79,7 +60,8 @@ struct Dit {
   void* w16_arena = nullptr;
   void* f32_arena = nullptr;
   // rotary tables for the last T used
-  float2* rope_cs = nullptr;
+  GrowBuf rope_buf;            // (cos, sin) [rope_T, rot/2]
+  float2* rope_cs = nullptr;   // = rope_buf.p
   int rope_T = 0;
   bool rope_dirty = true;
   // Two chunk pipelines ("lanes", like the VAE decoder's): consecutive sample chunks alternate between two workspaces
@@ -94,7 +76,6 @@ struct Dit {
   ~Dit() {
     if (w16_arena) cudaFree(w16_arena);
     if (f32_arena) cudaFree(f32_arena);
-    if (rope_cs) cudaFree(rope_cs);
     for (int l = 0; l < 2; ++l) {
       if (lane_stream[l]) cudaStreamDestroy(lane_stream[l]);
       if (lane_done[l]) cudaEventDestroy(lane_done[l]);
@@ -394,6 +375,25 @@ static size_t dit_workspace_bytes(const Dit* m, int B, int T) {
   return c.off + 4096;
 }
 
+// Rotary table for T tokens and workspaces for a batch of B samples (chunked): everything rgm_dit_forward allocates.
+static int dit_prepare(Dit* m, int B, int T, cudaStream_t st) {
+  if (m->rope_dirty || m->rope_T < T) {
+    if (m->rope_T < T) {
+      const int nf = m->rot / 2 > 0 ? m->rot / 2 : 1;
+      RGM_CUDA_OK(m->rope_buf.reserve((size_t)T * nf * sizeof(float2), st));
+      m->rope_cs = static_cast<float2*>(m->rope_buf.p);
+      m->rope_T = T;
+    }
+    if (m->rot > 0) RGM_CUDA_OK(launch_rope_table(m->rope_freqs, m->rope_cs, m->rope_T, m->rot / 2, st));
+    m->rope_dirty = false;
+  }
+  const int chunk = m->chunk < B ? m->chunk : B;
+  const int n_chunks = (B + chunk - 1) / chunk;
+  const int lanes = (m->n_lanes > 1 && n_chunks > 1) ? 2 : 1;
+  for (int l = 0; l < lanes; ++l) RGM_CUDA_OK(m->ws[l].reserve(dit_workspace_bytes(m, chunk, T), st));
+  return 0;
+}
+
 }  // namespace rgm
 
 using namespace rgm;
@@ -432,6 +432,14 @@ int rgm_dit_set_lanes(rgm_dit* h, int lanes) {
   if (!h) return set_error("rgm_dit_set_lanes: null handle");
   reinterpret_cast<Dit*>(h)->n_lanes = lanes >= 2 ? 2 : 1;
   return 0;
+}
+
+int rgm_dit_reserve(rgm_dit* h, int B, int H) {
+  if (rgm_check_device()) return -1;
+  if (!h) return set_error("rgm_dit_reserve: null handle");
+  Dit* m = reinterpret_cast<Dit*>(h);
+  if (B <= 0 || H <= 0) return 0;
+  return dit_prepare(m, B, H * m->tpt, nullptr);
 }
 
 int rgm_dit_destroy(rgm_dit* h) {
@@ -475,28 +483,15 @@ int rgm_dit_forward(rgm_dit* h, const float* x, const float* t, const long long*
   const int T = H * m->tpt;
   if (T != 128 && T != 256)
     return set_error("rgm_dit_forward: " + std::to_string(T) + " tokens; this build supports 128 or 256 (latent H 64 or 128 at patch 8)");
-  if (m->rope_dirty || m->rope_T < T) {
-    if (m->rope_T < T) {
-      if (m->rope_cs) {
-        cudaDeviceSynchronize();
-        cudaFree(m->rope_cs);
-      }
-      const int nf = m->rot / 2 > 0 ? m->rot / 2 : 1;
-      RGM_CUDA_OK(cudaMalloc(&m->rope_cs, (size_t)T * nf * sizeof(float2)));
-      m->rope_T = T;
-    }
-    if (m->rot > 0) RGM_CUDA_OK(launch_rope_table(m->rope_freqs, m->rope_cs, m->rope_T, m->rot / 2, st));
-    m->rope_dirty = false;
-  }
+  if (dit_prepare(m, B, T, st) != 0) return -1;
   const int chunk = m->chunk < B ? m->chunk : B;
   const int n_chunks = (B + chunk - 1) / chunk;
   const int lanes = (m->n_lanes > 1 && n_chunks > 1) ? 2 : 1;
-  for (int l = 0; l < lanes; ++l) RGM_CUDA_OK(m->ws[l].reserve(dit_workspace_bytes(m, chunk, T)));
   const long long per_in = (long long)m->C * H * m->W, per_out = (long long)m->Cout * H * m->W;
   if (lanes == 1) {
     for (int b0 = 0; b0 < B; b0 += chunk) {
       const int nb = (B - b0) < chunk ? (B - b0) : chunk;
-      if (dit_forward_chunk(m, m->ws[0].ptr, x + b0 * per_in, t + b0, y ? y + b0 : nullptr, out + b0 * per_out, nb, H,
+      if (dit_forward_chunk(m, m->ws[0].p, x + b0 * per_in, t + b0, y ? y + b0 : nullptr, out + b0 * per_out, nb, H,
                             st) != 0)
         return -1;
     }
@@ -514,7 +509,7 @@ int rgm_dit_forward(rgm_dit* h, const float* x, const float* t, const long long*
   for (int b0 = 0; b0 < B; b0 += chunk, ++ci) {
     const int nb = (B - b0) < chunk ? (B - b0) : chunk;
     const int l = ci & 1;
-    if (dit_forward_chunk(m, m->ws[l].ptr, x + b0 * per_in, t + b0, y ? y + b0 : nullptr, out + b0 * per_out, nb, H,
+    if (dit_forward_chunk(m, m->ws[l].p, x + b0 * per_in, t + b0, y ? y + b0 : nullptr, out + b0 * per_out, nb, H,
                           m->lane_stream[l]) != 0)
       return -1;
   }

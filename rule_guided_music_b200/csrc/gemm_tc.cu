@@ -106,14 +106,9 @@ std::atomic<unsigned long long> g_launches{0};
 template <int BN, int MT, int EPI>
 cudaError_t launch_inst(const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& p, int grid,
                         cudaStream_t stream) {
-  static bool attr_set = false;
+  static SmemAttr attr;
   auto kern = gemm_tc_kernel<BN, MT, EPI>;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)GemmCfg<BN, MT>::SMEM_BYTES);
-    if (e != cudaSuccess) return e;
-    attr_set = true;
-  }
+  if (cudaError_t e = attr.ensure(kern, GemmCfg<BN, MT>::SMEM_BYTES); e != cudaSuccess) return e;
   kern<<<grid, GEMM_THREADS, GemmCfg<BN, MT>::SMEM_BYTES, stream>>>(ma, mb, p);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return cudaGetLastError();
@@ -122,13 +117,9 @@ cudaError_t launch_inst(const CUtensorMap& ma, const CUtensorMap& mb, const Gemm
 template <int EPI>
 cudaError_t launch_sw(const CUtensorMap& mx, const CUtensorMap& mw, const GemmParams& p, int grid,
                       cudaStream_t stream) {
-  static bool attr_set = false;
+  static SmemAttr attr;
   auto kern = gemm_sw_kernel<EPI>;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SW_SMEM_BYTES);
-    if (e != cudaSuccess) return e;
-    attr_set = true;
-  }
+  if (cudaError_t e = attr.ensure(kern, SW_SMEM_BYTES); e != cudaSuccess) return e;
   kern<<<grid, GEMM_THREADS, SW_SMEM_BYTES, stream>>>(mx, mw, p);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return cudaGetLastError();
@@ -137,13 +128,9 @@ cudaError_t launch_sw(const CUtensorMap& mx, const CUtensorMap& mw, const GemmPa
 template <int EPI>
 cudaError_t launch_sw2(const CUtensorMap& mx, const CUtensorMap& mw, const GemmParams& p, int grid,
                        cudaStream_t stream) {
-  static bool attr_set = false;
+  static SmemAttr attr;
   auto kern = gemm_sw2_kernel<EPI>;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SW2_SMEM_BYTES);
-    if (e != cudaSuccess) return e;
-    attr_set = true;
-  }
+  if (cudaError_t e = attr.ensure(kern, SW2_SMEM_BYTES); e != cudaSuccess) return e;
   kern<<<grid, GEMM_THREADS, SW2_SMEM_BYTES, stream>>>(mx, mw, p);  // 2-CTA clusters (__cluster_dims__)
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return cudaGetLastError();

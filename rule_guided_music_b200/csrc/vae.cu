@@ -43,26 +43,7 @@ struct Res {
   bool has_nin = false;
 };
 
-struct DevBuf {
-  void* p = nullptr;
-  size_t bytes = 0;
-  cudaError_t reserve(size_t need) {
-    if (need <= bytes) return cudaSuccess;
-    if (p) {
-      cudaError_t e = cudaDeviceSynchronize();
-      if (e != cudaSuccess) return e;
-      cudaFree(p);
-      p = nullptr;
-      bytes = 0;
-    }
-    cudaError_t e = cudaMalloc(&p, need);
-    if (e == cudaSuccess) bytes = need;
-    return e;
-  }
-  ~DevBuf() {
-    if (p) cudaFree(p);
-  }
-};
+using DevBuf = GrowBuf;  // api_util.h: grows by retiring, never frees what a captured graph may reference
 
 }  // namespace
 
@@ -517,6 +498,31 @@ int encode_chunk(Vae* m, Vae::Lane* L, const float* x, float* moments, int t0, i
   return 0;
 }
 
+// largest activation of either network per tile, in elements: 128x128 pixels x (channels of level 1)
+long long vae_max_act(const Vae* m) {
+  long long maxc = 0;
+  for (int l = 0; l < m->n_levels; ++l) {
+    const long long hw = (long long)(16 << (m->n_levels - 1 - l)) * (16 << (m->n_levels - 1 - l));
+    const long long cmax = (long long)m->ch * m->mult[l < m->n_levels - 1 ? l + 1 : l];
+    maxc = std::max(maxc, hw * std::max(cmax, (long long)m->ch * m->mult[l]));
+  }
+  return std::max(maxc, 4LL * 256 * m->block_in0);  // the attention block carves 3-4 tensors out of one buffer
+}
+
+// Size the activation / statistics buffers of `lanes` lanes for chunks of `chunk` tiles.  Buffers only grow, and a
+// grown buffer's predecessor stays allocated (GrowBuf), so graphs captured earlier stay valid.
+int vae_reserve(Vae* m, int chunk, int lanes, cudaStream_t st) {
+  const long long maxc = vae_max_act(m);
+  for (int l = 0; l < lanes; ++l) {
+    Vae::Lane& L = m->lane[l];
+    for (int i = 0; i < 4; ++i) RGM_CUDA_OK(L.act[i].reserve((size_t)chunk * maxc * sizeof(__half), st));
+    RGM_CUDA_OK(L.gnpart.reserve((size_t)chunk * maxc / 8 + 1024, st));
+    RGM_CUDA_OK(L.abbuf.reserve((size_t)chunk * 512 * sizeof(float2) * 2, st));
+    RGM_CUDA_OK(L.attn_s.reserve((size_t)chunk * 256 * 256 * sizeof(float), st));
+  }
+  return 0;
+}
+
 }  // namespace
 }  // namespace rgm
 
@@ -563,6 +569,15 @@ int rgm_vae_set_lanes(rgm_vae* h, int lanes) {
   return 0;
 }
 
+int rgm_vae_reserve(rgm_vae* h, int n_tiles) {
+  if (!h) return set_error("rgm_vae_reserve: null handle");
+  Vae* m = reinterpret_cast<Vae*>(h);
+  if (n_tiles <= 0) return 0;
+  const int chunk = m->chunk_tiles < n_tiles ? m->chunk_tiles : n_tiles;
+  const int lanes = (m->n_lanes > 1 && n_tiles > chunk) ? 2 : 1;
+  return vae_reserve(m, chunk, lanes, nullptr);
+}
+
 int rgm_vae_destroy(rgm_vae* h) {
   if (h) {
     cudaDeviceSynchronize();
@@ -598,18 +613,8 @@ int rgm_vae_encode(rgm_vae* h, const float* x, float* moments, int n, void* stre
   if (n <= 0) return 0;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int chunk = m->chunk_tiles < n ? m->chunk_tiles : n;
-  long long maxc = 0;
-  for (int l = 0; l < m->n_levels; ++l) {
-    const long long hw = (long long)(16 << (m->n_levels - 1 - l)) * (16 << (m->n_levels - 1 - l));
-    const long long cmax = (long long)m->ch * m->mult[l < m->n_levels - 1 ? l + 1 : l];
-    maxc = std::max(maxc, hw * std::max(cmax, (long long)m->ch * m->mult[l]));
-  }
-  maxc = std::max(maxc, 4LL * 256 * m->block_in0);
+  if (vae_reserve(m, chunk, 1, st) != 0) return -1;
   Vae::Lane& L = m->lane[0];
-  for (int i = 0; i < 4; ++i) RGM_CUDA_OK(L.act[i].reserve((size_t)chunk * maxc * sizeof(__half)));
-  RGM_CUDA_OK(L.gnpart.reserve((size_t)chunk * maxc / 8 + 1024));
-  RGM_CUDA_OK(L.abbuf.reserve((size_t)chunk * 512 * sizeof(float2) * 2));
-  RGM_CUDA_OK(L.attn_s.reserve((size_t)chunk * 256 * 256 * sizeof(float)));
   for (int t0 = 0; t0 < n; t0 += chunk) {
     const int nt = (n - t0) < chunk ? (n - t0) : chunk;
     if (encode_chunk(m, &L, x, moments, t0, nt, st) != 0) return -1;
@@ -628,23 +633,9 @@ int rgm_vae_decode_latents(rgm_vae* h, const float* lat, float scale_factor, flo
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int total = n_cand * (Hlat / 16);
   const int chunk = m->chunk_tiles < total ? m->chunk_tiles : total;
-  // the largest activation of the decoder: 128x128 pixels x (channels of level 1) per tile
-  long long maxc = 0;
-  for (int l = 0; l < m->n_levels; ++l) {
-    const long long hw = (long long)(16 << (m->n_levels - 1 - l)) * (16 << (m->n_levels - 1 - l));
-    const long long cmax = (long long)m->ch * m->mult[l < m->n_levels - 1 ? l + 1 : l];
-    maxc = std::max(maxc, hw * std::max(cmax, (long long)m->ch * m->mult[l]));
-  }
-  maxc = std::max(maxc, 4LL * 256 * m->block_in0);  // the attention block carves 3-4 tensors out of one buffer
   const int n_chunks = (total + chunk - 1) / chunk;
   const int lanes = (m->n_lanes > 1 && n_chunks > 1) ? 2 : 1;
-  for (int l = 0; l < lanes; ++l) {
-    Vae::Lane& L = m->lane[l];
-    for (int i = 0; i < 4; ++i) RGM_CUDA_OK(L.act[i].reserve((size_t)chunk * maxc * sizeof(__half)));
-    RGM_CUDA_OK(L.gnpart.reserve((size_t)chunk * maxc / 8 + 1024));
-    RGM_CUDA_OK(L.abbuf.reserve((size_t)chunk * 512 * sizeof(float2) * 2));
-    RGM_CUDA_OK(L.attn_s.reserve((size_t)chunk * 256 * 256 * sizeof(float)));
-  }
+  if (vae_reserve(m, chunk, lanes, st) != 0) return -1;
   if (lanes == 1) {
     for (int t0 = 0; t0 < total; t0 += chunk) {
       const int nt = (total - t0) < chunk ? (total - t0) : chunk;

@@ -15,14 +15,15 @@ def _window_eps(eps_scalar_t_fn, xs, scalar_t, y, num_img, overlap_size):
     """xs ((b n), c, h, w) windows -> per-window eps with the overlap correction applied, same layout."""
     bn, c, h, w = xs.shape
     b = bn // num_img
-    if y is not None:
-        y = y.repeat_interleave(num_img)
-    t_rep = scalar_t.repeat_interleave(num_img)
-    full_eps = eps_scalar_t_fn(xs, t_rep, y=y).reshape(b, num_img, c, h, w).clone()
+    y_rep = None if y is None else y.repeat_interleave(num_img)
+    full_eps = eps_scalar_t_fn(xs, scalar_t.repeat_interleave(num_img), y=y_rep).reshape(b, num_img, c, h, w).clone()
     if num_img > 1:
-        keep = (th.arange(bn, device=xs.device) % num_img) != (num_img - 1)  # every window but the last of a sample
-        half_in = xs[keep][:, :, :, -overlap_size:].contiguous()
-        half_eps = eps_scalar_t_fn(half_in, t_rep[keep], y=None if y is None else y[keep])
+        # every window but the last of a sample, as static slices (a boolean mask would need a device->host sync for
+        # its size, which is also illegal inside a CUDA-graph capture); same row order as xs[keep]
+        half_in = xs.reshape(b, num_img, c, h, w)[:, :-1, :, :, -overlap_size:].reshape(b * (num_img - 1), c, h,
+                                                                                        overlap_size).contiguous()
+        y_half = None if y is None else y.repeat_interleave(num_img - 1)
+        half_eps = eps_scalar_t_fn(half_in, scalar_t.repeat_interleave(num_img - 1), y=y_half)
         full_eps[:, :-1, :, :, -overlap_size:] -= half_eps.reshape(b, num_img - 1, c, h, overlap_size)
     return full_eps.reshape(bn, c, h, w)
 

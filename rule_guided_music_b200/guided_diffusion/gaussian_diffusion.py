@@ -23,8 +23,12 @@ Quirks of the reference are preserved on purpose: candid
 passes the unwrapped model to scg_sample while ddim_sample wraps it; classifier guidance applies at every step when SCG
 is on; DDPM masks noise with t > t_end, DDIM with t != t_end; rules mutate the roll in place in dict order.
 """
+import collections
+import collections.abc
 import enum
+import functools
 import math
+import types
 
 import numpy as np
 import torch as th
@@ -132,8 +136,14 @@ _TABLES = ("betas", "alphas_cumprod", "alphas_cumprod_prev", "sqrt_alphas_cumpro
 
 
 class _StepGraph:
-    """One captured step: static input buffers, the graph, and the tensors it leaves its results in."""
-    __slots__ = ("graph", "x", "t", "out", "launches")
+    """One captured step: static input buffers, the graph, the tensors it leaves its results in, and strong references
+    to every object the signature identified by `id()` (a collected object's id can be reused by a different one, and a
+    graph replays with the addresses and Python constants it was captured with)."""
+    __slots__ = ("graph", "x", "t", "out", "launches", "refs")
+
+    def __init__(self, refs=None):
+        self.graph = self.x = self.t = self.out = self.launches = None
+        self.refs = refs
 
 
 class GaussianDiffusion:
@@ -170,7 +180,7 @@ class GaussianDiffusion:
         self._trace = None
         # CUDA-graph replay of whole steps (enable_cuda_graphs): signature -> _StepGraph
         self._graphs_on = False
-        self._graphs = {}
+        self._graphs = collections.OrderedDict()
 
     # ---- device-resident tables ----------------------------------------------------------------------------------
     def _tables(self, device):
@@ -320,9 +330,14 @@ class GaussianDiffusion:
             weight = float(scg_kwargs.get(rule_name, 1.))
             gen = func(roll)  # native rules launch their reduction kernels; user rules run as given
             kind = NATIVE_LOSS_KIND.get(loss_fn)
+            if kind == 1 and gen.dim() == 2 and gen.is_cuda and not gen.is_floating_point():
+                gen = gen.to(th.float32)  # class indices (note_density_class): exact in fp32, compared with !=
             if kind is not None and gen.dim() == 2 and gen.dtype == th.float32 and gen.is_cuda:
                 tgt = rule_target.to(dev, th.float32).contiguous()
                 gen = gen.contiguous()
+                if tuple(tgt.shape) != (B, gen.shape[1]):  # the kernel indexes target[(i % B) * K + k]
+                    raise _lib.RgmError(f"rule '{rule_name}': target shape {tuple(tgt.shape)} does not match the rule "
+                                        f"output [{B}, {gen.shape[1]}] (one row per sample)")
                 _lib.call("rgm_rule_loss_accum", _lib.ptr(gen), _lib.ptr(tgt), _lib.ptr(total), gen.shape[0], B,
                           gen.shape[1], kind, weight, stream)
                 each[rule_name] = (gen, tgt, loss_fn)
@@ -340,14 +355,19 @@ class GaussianDiffusion:
         """Fan each sample out to N candidate x_{t-1}, score their decoded x0 with the rules, keep the best.
         With dist_util.shard_candidates() on, this rank fans out, denoises, decodes and scores only its contiguous
         share of the N candidates and the ranks exchange their per-sample winners once (dist_util.first_max_over_ranks)."""
+        # g_coeff is exp(0.5*log_variance) or sigma expanded to x's shape: one value per sample for the fixed
+        # variances.  A learned (per-element) variance cannot reach this point in the reference either: its scg_sample
+        # fails the shape assert of _predict_xstart_from_eps on the 2C-channel model output (:519 -> :360).
+        if self.model_var_type in (ModelVarType.LEARNED, ModelVarType.LEARNED_RANGE):
+            raise AssertionError("scg_sample needs a fixed-variance diffusion (learn_sigma=False): the reference's "
+                                 "scg_sample asserts x_t.shape == eps.shape on a learn_sigma model's output")
         N = int(scg_kwargs["num_samples"])
         B = mean_pred.shape[0]
         dev = mean_pred.device
         elems = mean_pred[0].numel()
         stream = _lib.stream_ptr()
         mean_c = mean_pred.contiguous().float()
-        # g_coeff is exp(0.5*log_variance) or sigma expanded to x's shape: one value per sample
-        g = g_coeff.reshape(B, -1)[:, 0].contiguous().float()
+        g = g_coeff.reshape(B, -1)[:, 0].contiguous().float()  # fixed variances are one value per sample by construction
         noise = th.randn(N, *mean_pred.shape, device=dev, dtype=th.float32)  # same stream as randn_like(sample)
         shard = dist_util.candidate_sharding()
         n0, n1 = (0, N) if shard is None else dist_util.shard_range(N, shard[0], shard[1])
@@ -361,8 +381,7 @@ class GaussianDiffusion:
         del noise
         t_rep = t.repeat(Nl)
         eps = model(cand, self._scale_timesteps(t_rep), y=model_kwargs["y"].repeat(Nl))
-        if eps.shape[1] != cand.shape[1]:  # learn_sigma models: the mean half (reference splits in p_mean_variance only;
-            eps = eps[:, :cand.shape[1]]   # scg_sample would fail its shape assert there)
+        assert eps.shape == cand.shape, "scg_sample: the denoiser must return eps of the input's shape (reference :360)"
         tab = self._tables(dev)
         a = tab["sqrt_recip_alphas_cumprod"][t_rep].contiguous()
         c = tab["sqrt_recipm1_alphas_cumprod"][t_rep].contiguous()
@@ -461,7 +480,7 @@ class GaussianDiffusion:
         by the same offsets."""
         self._graphs_on = bool(on)
         if not on:
-            self._graphs = {}
+            self._graphs = collections.OrderedDict()
         return self
 
     def _graphable(self, x, kw):
@@ -474,7 +493,11 @@ class GaussianDiffusion:
             sh = dist_util.candidate_sharding()
             if sh is not None and dist_util.dist.get_backend(sh[2]) != "nccl":
                 return False  # the gloo exchange stages through the host
-            if not all(self._rule_is_native(n) and LOSS_DICT.get(n) in NATIVE_LOSS_KIND for n in mk.get("rule", {})):
+            rules = mk.get("rule", {})
+            if not all(self._rule_is_native(n) and LOSS_DICT.get(n) in NATIVE_LOSS_KIND for n in rules):
+                return False
+            # a target on the host would be copied in every step: a pageable copy is illegal inside a capture
+            if not all(isinstance(v, th.Tensor) and v.is_cuda for v in rules.values()):
                 return False
             em = kw["embed_model"]
             if em is not None and not hasattr(em, "decode_latents"):
@@ -482,45 +505,76 @@ class GaussianDiffusion:
         return True
 
     @staticmethod
-    def _sig(v):
-        """Hashable signature of a step argument: tensors by storage identity (a graph bakes their addresses in)."""
+    def _sig(v, refs):
+        """Hashable signature of a step argument.  Tensors by storage identity (a graph bakes their addresses in);
+        mappings, namespaces and functools.partial objects by CONTENT (a new partial with another cfg weight, or a
+        config object mutated in place, is a different step); everything else by identity, with a strong reference
+        appended to `refs` so that the id cannot be recycled while the cache entry lives."""
+        sig = GaussianDiffusion._sig
         if isinstance(v, th.Tensor):
+            refs.append(v)
             return ("T", v.data_ptr(), tuple(v.shape), str(v.dtype))
-        if isinstance(v, dict):
-            return tuple((k, GaussianDiffusion._sig(x)) for k, x in v.items())
         if isinstance(v, (int, float, str, bool)) or v is None:
             return v
-        return ("O", id(v))  # models, decoders: by identity
+        if isinstance(v, collections.abc.Mapping):
+            return ("M",) + tuple((str(k), sig(x, refs)) for k, x in v.items())
+        if isinstance(v, types.SimpleNamespace):
+            return ("N",) + tuple((k, sig(x, refs)) for k, x in sorted(vars(v).items()))
+        if isinstance(v, functools.partial):
+            return ("P", sig(v.func, refs), tuple(sig(a, refs) for a in v.args),
+                    tuple((k, sig(x, refs)) for k, x in sorted(v.keywords.items())))
+        if isinstance(v, (tuple, list)):
+            return ("L",) + tuple(sig(x, refs) for x in v)
+        refs.append(v)
+        return ("O", id(v))  # models, decoders, plain functions: by identity
+
+    MAX_STEP_GRAPHS = 8  # captured graphs kept (each pins its own memory pool); least recently used is released
 
     def _graphed_step(self, name, eager, model, x, t, t0, kw):
         # of guidance_kwargs a step reads the on/off decision (host-side, from t0) and the per-segment base length
         g = kw["guidance_kwargs"]
         dc_base = getattr(getattr(g, "dc", None), "base", 0)
         sh = dist_util.candidate_sharding()
-        key = (name, self._sig(model), tuple(x.shape), str(x.device), self._use_guidance(t0, g), dc_base,
-               None if sh is None else sh[:2],
-               t0 > self.t_end, self.t_end, tuple((k, self._sig(v)) for k, v in kw.items() if k != "guidance_kwargs"))
-        ent = self._graphs.get(key)
+        refs = []
+        key = (name, self._sig(model, refs), tuple(x.shape), str(x.device), self._use_guidance(t0, g), dc_base,
+               None if sh is None else sh[:2], t0 > self.t_end, self.t_end,
+               tuple((k, self._sig(v, refs)) for k, v in kw.items() if k != "guidance_kwargs"))
+        graphs = self._graphs
+        ent = graphs.get(key)
         if ent is None:
-            # first occurrence: eager (also grows the library's workspaces, which a capture must not do).  A caller
-            # that hands in freshly allocated tensors every step never repeats a signature: stop remembering after 64.
-            if len(self._graphs) < 64:
-                self._graphs[key] = False
+            # first occurrence: eager (it also grows the library's workspaces; growing under capture is refused).  The
+            # placeholder keeps the references too, so the key cannot be matched by recycled ids.
+            graphs[key] = _StepGraph(refs)
+            self._evict_graphs()
             return eager(model, x, t, t0, **kw)
-        if ent is False:
-            ent = _StepGraph()
+        graphs.move_to_end(key)
+        if ent.graph is None:
             ent.x = x.clone()
             ent.t = t.clone()
             th.cuda.synchronize(x.device)
-            ent.graph = th.cuda.CUDAGraph()
-            with th.cuda.graph(ent.graph):
+            graph = th.cuda.CUDAGraph()
+            with th.cuda.graph(graph):
                 ent.out = eager(model, ent.x, ent.t, t0, **kw)
-            ent.launches = None
-            self._graphs[key] = ent
+            ent.graph = graph
+            self._evict_graphs()
         ent.x.copy_(x)
         ent.t.copy_(t)
         ent.graph.replay()
         return {k: v.clone() for k, v in ent.out.items()}
+
+    def captured_graphs(self):
+        """Number of step kinds currently held as captured CUDA graphs."""
+        return sum(1 for e in self._graphs.values() if e.graph is not None)
+
+    def _evict_graphs(self):
+        """Bound the cache: at most MAX_STEP_GRAPHS captured graphs and 64 entries in total (a caller that hands in
+        freshly allocated tensors every step never repeats a signature)."""
+        graphs = self._graphs
+        captured = [k for k, e in graphs.items() if e.graph is not None]
+        while len(captured) > self.MAX_STEP_GRAPHS:
+            graphs.pop(captured.pop(0))  # dropping the entry releases the CUDAGraph and its private pool
+        while len(graphs) > 64:
+            graphs.popitem(last=False)
 
     # ---- one ancestral step (reference :635-735) -----------------------------------------------------------------
     @staticmethod

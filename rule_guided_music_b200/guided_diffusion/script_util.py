@@ -73,7 +73,10 @@ def add_dict_to_argparser(parser, default_dict):
             v_type = str
         elif isinstance(v, bool):
             v_type = str2bool
-        parser.add_argument(f"--{k}", default=v, type=v_type)
+        if k == "image_size":  # `--image_size 128 16`: scripts index args.image_size[0] / [1] (reference :510-511)
+            parser.add_argument(f"--{k}", nargs="+", default=v, type=v_type)
+        else:
+            parser.add_argument(f"--{k}", default=v, type=v_type)
 
 
 def args_to_dict(args, keys):

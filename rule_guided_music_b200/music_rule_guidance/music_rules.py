@@ -34,10 +34,16 @@ def total_pitch_class_histogram(piano_roll):
 
 
 def note_density(piano_roll, interval=128, quantize_factor=1, horizontal_scale=5):
-    """music_rules.py:46-83 (quantize_factor = 1, which is what every registered rule uses)."""
-    if quantize_factor != 1:
-        raise NotImplementedError("note_density(quantize_factor != 1) is not on the B200 path")
+    """music_rules.py:46-83.  quantize_factor != 1 (:59-61) first resamples the time axis with
+    F.interpolate(mode="nearest") to L // quantize_factor columns -- for L divisible by the factor that is every
+    quantize_factor-th column, and a NEW tensor, so the in-place threshold does not reach the caller's roll."""
     _check(piano_roll)
+    if quantize_factor != 1:
+        q = int(quantize_factor)
+        if q < 1 or piano_roll.shape[-1] % q != 0 or interval % q != 0:
+            raise _lib.RgmError("note_density: quantize_factor must divide the roll length and the interval")
+        piano_roll = piano_roll[:, :1, :, ::q].contiguous()
+        interval = interval // q
     B, C, _, L = piano_roll.shape
     out = torch.empty(B, 2 * (L // interval), device=piano_roll.device, dtype=torch.float32)
     with torch.cuda.device(piano_roll.device):
@@ -46,12 +52,26 @@ def note_density(piano_roll, interval=128, quantize_factor=1, horizontal_scale=5
     return out.squeeze(0) if B == 1 else out
 
 
+_BOUNDS = {}  # (device, horizontal_scale) -> (vertical, horizontal) class bounds on that device
+
+
+def _class_bounds(device, horizontal_scale):
+    """The bucket bounds as device tensors, built once per device: creating them per call is a pageable host-to-device
+    copy, which synchronises and is illegal while a CUDA graph is being captured."""
+    key = (str(device), float(horizontal_scale))
+    b = _BOUNDS.get(key)
+    if b is None:
+        b = (torch.tensor(VERTICAL_ND_BOUNDS, device=device),
+             torch.tensor(HORIZONTAL_ND_BOUNDS, device=device) / horizontal_scale)
+        _BOUNDS[key] = b
+    return b
+
+
 def note_density_class(piano_roll, interval=128, quantize_factor=1, horizontal_scale=1):
     """music_rules.py:86-94 (bucketize on the fixed class bounds)."""
     nd = note_density(piano_roll, interval=interval, quantize_factor=quantize_factor,
                       horizontal_scale=horizontal_scale)
-    vt = torch.tensor(VERTICAL_ND_BOUNDS, device=nd.device)
-    hr = torch.tensor(HORIZONTAL_ND_BOUNDS, device=nd.device) / horizontal_scale
+    vt, hr = _class_bounds(nd.device, horizontal_scale)
     n = nd.shape[-1]
     return torch.cat((torch.bucketize(nd[:, :n // 2].contiguous(), vt), torch.bucketize(nd[:, n // 2:].contiguous(), hr)),
                      dim=-1)

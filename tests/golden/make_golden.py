@@ -78,6 +78,12 @@ def golden_rules():
                 out[f"{case}__{name}"] = FUNC_DICT[name](roll.clone()).numpy()
             except IndexError:  # note_density_class on a B == 1 roll: the reference indexes a squeezed tensor
                 out[f"{case}__{name}__raises"] = 1
+    # quantize_factor != 1 (music_rules.py:59-61): nearest resampling of the time axis first, input left untouched
+    from music_rule_guidance.music_rules import note_density as ref_note_density
+    for q in gi.RULE_QUANT:
+        r = gi.rule_rolls()["random"]
+        out[f"random__note_density_q{q}"] = ref_note_density(r, quantize_factor=q).numpy()
+        out[f"random__note_density_q{q}__input_untouched"] = int(torch.equal(r, gi.rule_rolls()["random"]))
     # order dependence: pitch_hist evaluated after note_density on the SAME tensor (in-place threshold)
     r = gi.rule_rolls()["order"]
     FUNC_DICT["note_density"](r)
@@ -316,8 +322,80 @@ def golden_sampler_ext():
     out["midi_roll"] = decode_sample_for_midi(gi.vae_latents(), embed, gi.SCALE_FACTOR, threshold=-0.95).numpy()
     save("sampler_ext", **out)
 
+def golden_flagship():
+    """BASELINE config 3's step at B = 1 through the unmodified reference (gaussian_diffusion.py:881-976 -> :491-554):
+    XL/8 denoiser, N = 16 candidates, 128 VAE tiles, pitch-histogram scores, argmax, teacher-forced at two timesteps."""
+    cfg = gi.FLAGSHIP
+    embed = build_ref_vae()
+    model, _ = build_ref_dit(gi.DIT_CASES[cfg["dit"]])
+    diffusion = create_diffusion(timestep_respacing=cfg["respacing"])
+    cap = {}
+
+    def spy_model(x, t, *a, **kw):
+        o = model(x, t, *a, **kw)
+        cap["eps" if x.shape[0] > 1 else "eps_b"] = o.clone()
+        if x.shape[0] > 1:
+            cap["cand"], cap["t_model"] = x.clone(), t.clone()
+        return o
+
+    real_decode, real_scg = gd._decode, diffusion.scg_sample
+    real_func, real_loss = gd.FUNC_DICT["pitch_hist"], gd.LOSS_DICT["pitch_hist"]
+
+    def spy_decode(z, em, scale_factor=1., threshold=False):
+        cap["x0"] = z.clone()
+        roll = real_decode(z, em, scale_factor=scale_factor, threshold=threshold)
+        cap["roll"] = roll.clone()  # before the rules mask it in place
+        return roll
+
+    def spy_scg(m, t, mean_pred, g_coeff, *a, **k):
+        cap["mean_pred"], cap["g"] = mean_pred.clone(), g_coeff.reshape(mean_pred.shape[0], -1)[:, 0].clone()
+        return real_scg(m, t, mean_pred, g_coeff, *a, **k)
+
+    def spy_func(roll):
+        cap["hist"] = real_func(roll).clone()
+        return cap["hist"]
+
+    def spy_loss(gen, y):
+        cap["loss"] = real_loss(gen, y).clone()
+        return cap["loss"]
+
+    gd._decode, diffusion.scg_sample = spy_decode, spy_scg
+    gd.FUNC_DICT["pitch_hist"], gd.LOSS_DICT["pitch_hist"] = spy_func, spy_loss
+    fn = partial(model_fn, model=spy_model, num_classes=3, class_cond=True, cfg=False, w=0.0)
+    out = {}
+    try:
+        for case, c in cfg["cases"].items():
+            x_t, t = gi.flagship_inputs(case, diffusion.alphas_cumprod)
+            kwargs = {"y": torch.ones(1, dtype=torch.long), "rule": gi.rule_targets(1, 1024, cfg["rules"])}
+            torch.manual_seed(c["seed"])
+            diffusion.t_end = 0
+            o = diffusion.ddim_sample(fn, x_t, t, model_kwargs=kwargs, eta=cfg["eta"], embed_model=embed,
+                                      scale_factor=gi.SCALE_FACTOR, guidance_kwargs=SimpleNamespace(**cfg["guidance"]),
+                                      scg_kwargs=dict(cfg["scg"]))
+            total = (-cap["loss"] * cfg["scg"]["pitch_hist"]).view(cfg["N"], -1)
+            out[case + "__t_model"] = cap["t_model"].numpy()          # original-scale timestep the denoiser saw
+            out[case + "__eps_b"] = cap["eps_b"].numpy()              # the B = 1 pass of p_mean_variance
+            out[case + "__pred_xstart"] = o["pred_xstart"].numpy()
+            out[case + "__mean_pred"] = cap["mean_pred"].numpy()
+            out[case + "__g"] = cap["g"].numpy()
+            out[case + "__cand_sub"] = cap["cand"][:, :, ::2].numpy()  # every other time step: fixture size
+            out[case + "__eps_sub"] = cap["eps"][:, :, ::2].numpy()
+            out[case + "__x0_sub"] = cap["x0"][:, :, ::2].numpy()
+            out[case + "__roll_sub"] = cap["roll"][:, 0, ::4, ::8].numpy()
+            out[case + "__roll_stats"] = np.array([cap["roll"][:, 0].mean().item(), cap["roll"][:, 0].std().item(),
+                                                   (cap["roll"][:, 0] > -0.95).float().mean().item()])
+            out[case + "__hist"] = cap["hist"].numpy()
+            out[case + "__total"] = total.numpy()
+            out[case + "__max_ind"] = total.argmax(dim=0).numpy()
+            out[case + "__sample"] = o["sample"].numpy()
+            print(case, "totals", total.view(-1).numpy(), "argmax", int(total.argmax(dim=0)))
+    finally:
+        gd._decode, diffusion.scg_sample = real_decode, real_scg
+        gd.FUNC_DICT["pitch_hist"], gd.LOSS_DICT["pitch_hist"] = real_func, real_loss
+    save("flagship", **out)
+
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["schedule", "rules", "dit", "vae", "vae_enc", "collage", "host", "sampler", "sampler_ext"]
+    which = sys.argv[1:] or ["schedule", "rules", "dit", "vae", "vae_enc", "collage", "host", "sampler", "sampler_ext", "flagship"]
     for w in which:
         globals()["golden_" + w]()

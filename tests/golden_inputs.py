@@ -17,6 +17,8 @@ SCHEDULE_KEYS = [
 RULE_NAMES = ["pitch_hist", "note_density", "note_density_hr_1", "note_density_hr_2", "note_density_class",
               "note_density_pixel"]
 
+RULE_QUANT = [2, 4]  # note_density(quantize_factor=...) cases
+
 # ---------------------------------------------------------------------------------------------------------------
 # DiT
 # ---------------------------------------------------------------------------------------------------------------
@@ -262,3 +264,26 @@ HOST_CASES = {
     "ddpm_no_clip": dict(respacing="4", ddim=False, seed=87, clip=False),
 }
 HOST_SHAPE = (2, 4, 32, 16)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# flagship step (BASELINE.json config 3's model and guidance at B = 1): DiTRotary_XL_8, DDIM(eta=1), respacing "256",
+# SCG N = 16, pitch histogram.  ONE teacher-forced ddim_sample call per case through the unmodified reference with
+# every stage of scg_sample captured (tests/golden/flagship.npz); the GPU test replays the same noise and compares
+# stage by stage.
+# ---------------------------------------------------------------------------------------------------------------
+FLAGSHIP = dict(dit="xl8", respacing="256", eta=1.0, N=16, rules=["pitch_hist"],
+                scg=dict(num_samples=16, pitch_hist=1.0), guidance=_GUIDE_ON,
+                # spaced timestep index (of 256) -> original timestep 4 * idx (respace.py:38-60): t = 900 and t = 200
+                cases={"t900": dict(t_index=225, seed=41), "t200": dict(t_index=50, seed=42)})
+
+
+def flagship_inputs(case, alphas_cumprod):
+    """x_t [1,4,128,16] for the spaced step index of `case`: a seeded latent-like x0 noised to that level
+    (`alphas_cumprod` = the SPACED diffusion's table, float64 numpy)."""
+    c = FLAGSHIP["cases"][case]
+    g = torch.Generator(device="cpu").manual_seed(c["seed"])
+    x0 = torch.randn(1, 4, 128, 16, generator=g) * 0.8
+    ab = float(alphas_cumprod[c["t_index"]])
+    x_t = ab ** 0.5 * x0 + (1 - ab) ** 0.5 * torch.randn(1, 4, 128, 16, generator=g)
+    return x_t.float(), torch.tensor([c["t_index"]], dtype=torch.long)

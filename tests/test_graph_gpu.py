@@ -46,8 +46,7 @@ def test_graph_replay_is_bit_identical_to_eager(cuda, ddim, scg):
     graphed, diffusion = _run(cuda, model, vae, True, ddim, scg)
     assert len(eager) == len(graphed) == 8
     # steps 7..1 share one signature (first eager, then captured + replayed), step 0 is its own kind
-    captured = [g for g in diffusion._graphs.values() if g is not False]
-    assert len(captured) == 1
+    assert diffusion.captured_graphs() == 1
     for i, (a, b) in enumerate(zip(eager, graphed)):
         assert torch.equal(a, b), f"step {i}: max abs diff {(a - b).abs().max().item():.3e}"
     assert all(torch.isfinite(s).all() for s in graphed)

@@ -24,7 +24,7 @@ GOLD = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"
 
 
 @pytest.mark.parametrize("tag", list(gi.EXT_CASES))
-def test_extended_trajectory_matches_reference(cuda, tag):
+def test_extended_trajectory_matches_reference(cuda, tag, parity):
     cfg = gi.EXT_CASES[tag]
     model, _ = gpu_util.native_dit(gi.DIT_CASES[cfg["dit"]], cuda)
     vae, _ = gpu_util.native_vae(cuda)
@@ -96,6 +96,9 @@ def test_extended_trajectory_matches_reference(cuda, tag):
                 errs.append(err)
             assert torch.isfinite(out["sample"]).all()
             img = ref[k].to(cuda)
+    parity(f"teacher-forced {tag}: candidate scores (max over decisions)", max(score_errs + [0.0]), 5e-3, "rel-max")
+    for i, e in enumerate(errs):
+        parity(f"teacher-forced {tag}: x_(t-1) of decisive step {i}", e, 1e-2)
     assert max(score_errs + [0.0]) < 5e-3, score_errs     # candidate scores: fp16 decoder vs fp32 reference
     assert len(errs) >= 1 and max(errs) < 1e-2, (errs, score_errs)
 

@@ -24,7 +24,7 @@ GOLD = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"
 
 
 @pytest.mark.parametrize("tag", list(gi.SAMPLER_CASES))
-def test_trajectory_matches_reference(cuda, tag):
+def test_trajectory_matches_reference(cuda, tag, parity):
     cfg = gi.SAMPLER_CASES[tag]
     model, _ = gpu_util.native_dit(gi.DIT_CASES[cfg["dit"]], cuda)
     vae, _ = gpu_util.native_vae(cuda)
@@ -46,4 +46,6 @@ def test_trajectory_matches_reference(cuda, tag):
     ref = torch.from_numpy(GOLD[tag])
     assert len(steps) == ref.shape[0]
     errs = [gpu_util.rel_l2(s, r) for s, r in zip(steps, ref)]
+    for i, e in enumerate(errs):
+        parity(f"free-running trajectory {tag}, x_t after step {i}", e, 1e-2)
     assert max(errs) < 1e-2, errs

@@ -17,24 +17,25 @@ pytestmark = pytest.mark.gpu
 GOLD = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "vae.npz"))
 
 
-def test_decode_tiles_matches_reference(cuda):
+def test_decode_tiles_matches_reference(cuda, parity):
     vae, _ = gpu_util.native_vae(cuda)
     out = vae.decode(gi.vae_tiles().to(cuda)).cpu()
     ref = torch.from_numpy(GOLD["tiles"])
     assert out.shape == ref.shape
-    err = gpu_util.rel_l2(out, ref)
-    flips = ((out >= -0.95) != (ref >= -0.95)).float().mean().item()
+    err = parity("VAE decode, 2 tiles", gpu_util.rel_l2(out, ref), 5e-3)
+    flips = parity("VAE decode, note-threshold flips", ((out >= -0.95) != (ref >= -0.95)).float().mean().item(), 5e-3,
+                   "fraction")
     assert err < 5e-3, err
     assert flips < 5e-3, flips
 
 
-def test_decode_latents_layout_and_chunking(cuda, monkeypatch):
+def test_decode_latents_layout_and_chunking(cuda, monkeypatch, parity):
     """_decode's tile-major re-tiling: roll[b, :, :, k*128:(k+1)*128] is tile k of sample b; chunked == unchunked."""
     vae, sd = gpu_util.native_vae(cuda)
     lat = gi.vae_latents()
     roll = vae.decode_latents(lat.to(cuda), gi.SCALE_FACTOR).cpu()
     ref_sub = torch.from_numpy(GOLD["decode_latents_sub4"])
-    assert gpu_util.rel_l2(roll[:, :, ::4, ::4], ref_sub) < 5e-3
+    assert parity("_decode roll (sub-sampled)", gpu_util.rel_l2(roll[:, :, ::4, ::4], ref_sub), 5e-3) < 5e-3
     monkeypatch.setenv("RGM_VAE_CHUNK", "3")
     vae2, _ = gpu_util.native_vae(cuda)
     roll2 = vae2.decode_latents(lat.to(cuda), gi.SCALE_FACTOR).cpu()
@@ -43,7 +44,7 @@ def test_decode_latents_layout_and_chunking(cuda, monkeypatch):
     assert torch.equal(ch0[:, 0], roll[:, 0])
 
 
-def test_decode_many_tiles_vs_oracle(cuda):
+def test_decode_many_tiles_vs_oracle(cuda, parity):
     """More tiles than one chunk, random latents, against the oracle run on the CPU here."""
     vae, sd = gpu_util.native_vae(cuda)
     g = torch.Generator(device="cpu").manual_seed(9)
@@ -58,7 +59,7 @@ def test_decode_many_tiles_vs_oracle(cuda):
 GOLD_ENC = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "vae_enc.npz"))
 
 
-def test_encode_matches_reference(cuda):
+def test_encode_matches_reference(cuda, parity):
     """Encoder + quant_conv (stride-2 implicit-GEMM Downsample, fp32 stem and tail) vs the reference's moments, and
     _encode's re-tiling vs the reference's latents.  Same precision policy and bar as the decoder (5e-3 rel L2)."""
     from rule_guided_music_b200.guided_diffusion.gaussian_diffusion import _encode
@@ -69,11 +70,11 @@ def test_encode_matches_reference(cuda):
     moments = vae.encode_save(tiles.to(cuda)).cpu()
     ref = torch.from_numpy(GOLD_ENC["moments"])
     assert moments.shape == ref.shape
-    assert gpu_util.rel_l2(moments, ref) < 5e-3, gpu_util.rel_l2(moments, ref)
+    assert parity("VAE encoder moments", gpu_util.rel_l2(moments, ref), 5e-3) < 5e-3
     lat = _encode(rolls.to(cuda), vae, scale_factor=gi.SCALE_FACTOR).cpu()
     ref_lat = torch.from_numpy(GOLD_ENC["encode_latents"])
     assert lat.shape == ref_lat.shape
-    assert gpu_util.rel_l2(lat, ref_lat) < 5e-3
+    assert parity("_encode latents", gpu_util.rel_l2(lat, ref_lat), 5e-3) < 5e-3
     post = vae.encode(tiles.to(cuda))
     assert torch.equal(post.mode().cpu(), moments[:, :4])
     assert post.sample().shape == (4, 4, 16, 16)

@@ -188,6 +188,15 @@ int rgm_gemm_f16(const void* a16, const void* b16, const float* bias, float* out
  * x16 [n,H,W,Cin], out16 [n,H',W',Cout], optional resid16 like out16; gn_part may be NULL */
 int rgm_conv_f16(const void* x16, const void* w16_packed, const float* bias, const void* resid16, void* out16,
                  int n_img, int H, int W, int Cin, int Cout, int kind, int block_n, float* gn_part, void* stream);
+/* GroupNorm apply (+ swish) as its own pass: y16 = swish(a*x16 + b) with ab = (a, b) f32 pairs per (image, channel)
+ * (reference model.py:34-35, 29-31, the `h = nonlinearity(norm(x))` of ResnetBlock :119-120) */
+int rgm_gn_apply_f16(const void* x16, const float* ab, void* y16, int n_img, int HW, int C, int swish, void* stream);
+/* conv3x3(swish(GroupNorm(x))) in ONE kernel (reference model.py:117-137): x16_raw is the un-normalised NHWC tensor
+ * [n, H, 128, Cin], ab_in its GroupNorm affine [n][Cin] (a, b); weights / bias / residual / output / gn_part as in
+ * rgm_conv_f16 with kind 1.  W must be 128, H even, Cout 128. */
+int rgm_conv_gn_f16(const void* x16_raw, const float* ab_in, const void* w16_packed, const float* bias,
+                    const void* resid16, void* out16, int n_img, int H, int W, int Cin, int Cout, float* gn_part,
+                    void* stream);
 /* weight fp32 [Cout,Cin,kh,kw] (torch layout) -> packed fp16 rows for rgm_conv_f16; cin_pad >= Cin (multiple of 64),
  * cout_pad >= Cout. Output size: kind 0: cout_pad*cin_pad; kind 1, 3: cout_pad*9*cin_pad; kind 2: 4*cout_pad*4*cin_pad */
 int rgm_pack_conv_weight(const float* w32, void* w16_packed, int Cout, int Cin, int cout_pad, int cin_pad, int kind,

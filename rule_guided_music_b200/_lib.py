@@ -83,6 +83,9 @@ _SIGNATURES = {
     "rgm_gemm_f16": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
     "rgm_conv_f16": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
                      c_int, c_void_p, c_void_p],
+    "rgm_gn_apply_f16": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
+    "rgm_conv_gn_f16": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
+                        c_void_p, c_void_p],
     "rgm_pack_conv_weight": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p],
     "rgm_attention_f16": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p],
 }

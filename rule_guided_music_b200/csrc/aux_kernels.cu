@@ -143,10 +143,120 @@ __global__ void __launch_bounds__(256) ln_modulate_kernel(const float* __restric
   }
 }
 
+// Two rows per warp.  Rows 2k and 2k+1 are adjacent in memory, so the warp streams 2*D contiguous floats: lane l owns
+// the 8-element chunks l, l + 32, ... (NV of them) -- two 16-byte loads in, ONE 16-byte store out per chunk (the one-row
+// kernel above stores 8 bytes per lane and keeps half as many loads in flight; it measured 3.6 TB/s = 0.55 of the copy
+// peak).  Same arithmetic per element; the two rows' statistics are kept apart by the chunk's row.
+template <int NV, int OCC>
+__global__ void __launch_bounds__(256, OCC) ln_modulate2_kernel(const float* __restrict__ x, const float* __restrict__ shift,
+                                                              const float* __restrict__ scale, int mod_ld,
+                                                              __half* __restrict__ out, long long pairs,
+                                                              int rows_per_sample, float eps) {
+  constexpr int D = NV * 128;
+  constexpr int CPR = D / 8;  // chunks per row
+  const int lane = threadIdx.x & 31;
+  const long long warp0 = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long pr = warp0; pr < pairs; pr += nwarps) {
+    const long long row0 = 2 * pr;
+    const float4* xp = reinterpret_cast<const float4*>(x + row0 * D);
+    float4 v[NV][2];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      v[i][0] = xp[(lane + 32 * i) * 2];
+      v[i][1] = xp[(lane + 32 * i) * 2 + 1];
+    }
+    float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const float cs = ((v[i][0].x + v[i][0].y) + (v[i][0].z + v[i][0].w)) + ((v[i][1].x + v[i][1].y) + (v[i][1].z + v[i][1].w));
+      if (lane + 32 * i >= CPR) s1 += cs;
+      else s0 += cs;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+      s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+    }
+    const float m0 = s0 * (1.0f / D), m1 = s1 * (1.0f / D);
+    float q0 = 0.f, q1 = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const bool r1 = lane + 32 * i >= CPR;
+      const float m = r1 ? m1 : m0;
+      float cq = 0.f;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const float a = v[i][h].x - m, b = v[i][h].y - m, c = v[i][h].z - m, d = v[i][h].w - m;
+        cq += (a * a + b * b) + (c * c + d * d);
+      }
+      if (r1) q1 += cq;
+      else q0 += cq;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      q0 += __shfl_xor_sync(0xffffffffu, q0, o);
+      q1 += __shfl_xor_sync(0xffffffffu, q1, o);
+    }
+    const float rs0 = rsqrtf(q0 * (1.0f / D) + eps), rs1 = rsqrtf(q1 * (1.0f / D) + eps);
+    const long long b = row0 / rows_per_sample;  // both rows belong to one sample (rows_per_sample is even)
+    const float4* sh = reinterpret_cast<const float4*>(shift + b * mod_ld);
+    const float4* sc = reinterpret_cast<const float4*>(scale + b * mod_ld);
+    uint4* o4 = reinterpret_cast<uint4*>(out + row0 * D);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = lane + 32 * i;
+      const bool r1 = c >= CPR;
+      const float m = r1 ? m1 : m0, rstd = r1 ? rs1 : rs0;
+      const int off = (r1 ? c - CPR : c) * 2;  // float4 index inside the row
+      uint4 u;
+      uint32_t* uw = reinterpret_cast<uint32_t*>(&u);
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const float4 hh = __ldg(sh + off + h);
+        const float4 cc = __ldg(sc + off + h);
+        const float y0 = (v[i][h].x - m) * rstd * (1.f + cc.x) + hh.x;
+        const float y1 = (v[i][h].y - m) * rstd * (1.f + cc.y) + hh.y;
+        const float y2 = (v[i][h].z - m) * rstd * (1.f + cc.z) + hh.z;
+        const float y3 = (v[i][h].w - m) * rstd * (1.f + cc.w) + hh.w;
+        __half2 p0 = __floats2half2_rn(y0, y1), p1 = __floats2half2_rn(y2, y3);
+        uw[2 * h] = *reinterpret_cast<uint32_t*>(&p0);
+        uw[2 * h + 1] = *reinterpret_cast<uint32_t*>(&p1);
+      }
+      o4[c] = u;
+    }
+  }
+}
+
 cudaError_t launch_ln_modulate(const float* x, const float* shift, const float* scale, int mod_ld, __half* out,
                                long long rows, int D, int rows_per_sample, float eps, cudaStream_t s) {
-  const int grid = blocks_for(rows, 8, 148 * 8);
+  if (D % 128 != 0) return cudaErrorInvalidValue;
   ProfScope prof("ln_modulate", 0, 0, (double)rows * D * 6.0, s);
+  static const int one_row = [] {
+    const char* e = getenv("RGM_LN_ONE_ROW");  // development knob: the one-row-per-warp kernel
+    return e ? atoi(e) : 0;
+  }();
+  static const int occ2 = [] {
+    const char* e = getenv("RGM_LN_OCC");  // 2 (default): 128 registers, two blocks per SM, 48 B of spills: 4.0 TB/s;
+    return e ? atoi(e) == 2 : 1;           // 1: 246 registers, one block per SM: 3.6 TB/s (B200, config 2)
+  }();
+  if (!one_row && rows % 2 == 0 && rows_per_sample % 2 == 0 && mod_ld % 4 == 0) {
+    const long long pairs = rows / 2;
+    const int grid = blocks_for(pairs, 8, 148 * 8);
+#define RGM_LN2(NV)                                                                                                   \
+  case NV:                                                                                                            \
+    if (occ2) ln_modulate2_kernel<NV, 2><<<grid, 256, 0, s>>>(x, shift, scale, mod_ld, out, pairs, rows_per_sample, eps); \
+    else ln_modulate2_kernel<NV, 1><<<grid, 256, 0, s>>>(x, shift, scale, mod_ld, out, pairs, rows_per_sample, eps);      \
+    break;
+    switch (D / 128) {
+      RGM_LN2(2) RGM_LN2(3) RGM_LN2(4) RGM_LN2(6) RGM_LN2(8) RGM_LN2(9)
+      default:
+        return cudaErrorInvalidValue;
+    }
+#undef RGM_LN2
+    return done();
+  }
+  const int grid = blocks_for(rows, 8, 148 * 8);
 #define RGM_LN(NV)                                                                                                   \
   case NV:                                                                                                           \
     ln_modulate_kernel<NV><<<grid, 256, 0, s>>>(x, shift, scale, mod_ld, out, rows, rows_per_sample, eps);           \
@@ -157,7 +267,6 @@ cudaError_t launch_ln_modulate(const float* x, const float* shift, const float* 
       return cudaErrorInvalidValue;
   }
 #undef RGM_LN
-  if (D % 128 != 0) return cudaErrorInvalidValue;
   return done();
 }
 

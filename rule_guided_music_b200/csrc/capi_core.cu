@@ -233,6 +233,47 @@ int rgm_conv_f16(const void* x16, const void* w16_packed, const float* bias, con
   return 0;
 }
 
+int rgm_gn_apply_f16(const void* x16, const float* ab, void* y16, int n_img, int HW, int C, int swish, void* stream) {
+  if (rgm_check_device()) return -1;
+  if (!x16 || !ab || !y16) return set_error("rgm_gn_apply_f16: null argument");
+  return check_cuda(launch_gn_apply(static_cast<const __half*>(x16), reinterpret_cast<const float2*>(ab),
+                                    static_cast<__half*>(y16), n_img, HW, C, swish, static_cast<cudaStream_t>(stream)),
+                    "rgm_gn_apply_f16");
+}
+
+int rgm_conv_gn_f16(const void* x16_raw, const float* ab_in, const void* w16_packed, const float* bias,
+                    const void* resid16, void* out16, int n_img, int H, int W, int Cin, int Cout, float* gn_part,
+                    void* stream) {
+  if (rgm_check_device()) return -1;
+  if (!x16_raw || !ab_in || !w16_packed || !out16) return set_error("rgm_conv_gn_f16: null argument");
+  GemmDesc d;
+  d.A = static_cast<const __half*>(x16_raw);
+  d.n_img = n_img;
+  d.H = H;
+  d.W = W;
+  d.C = Cin;
+  d.lda = Cin;
+  d.B = static_cast<const __half*>(w16_packed);
+  d.N = Cout;
+  d.rows_b = Cout;
+  d.conv = CONV_3x3;
+  d.epi = EPI_F16;
+  d.e.out = out16;
+  d.e.ldo = Cout;
+  d.e.bias = bias;
+  d.e.alpha = 1.f;
+  d.e.resid = static_cast<const __half*>(resid16);
+  d.e.ldr = Cout;
+  d.e.gn_part = gn_part;
+  if (const char* tr = getenv("RGM_DEBUG_TRACE_PTR")) d.trace = reinterpret_cast<unsigned long long*>(strtoull(tr, nullptr, 0));
+  if (!conv_gn_shape_ok(d))
+    return set_error("rgm_conv_gn_f16: needs a 3x3 conv on [n, H even, 128, Cin % 64 == 0] with 128 output features");
+  std::string err;
+  if (launch_conv_gn(d, reinterpret_cast<const float2*>(ab_in), static_cast<cudaStream_t>(stream), &err) != cudaSuccess)
+    return set_error(err);
+  return 0;
+}
+
 int rgm_pack_conv_weight(const float* w32, void* w16_packed, int Cout, int Cin, int cout_pad, int cin_pad, int kind,
                          void* stream) {
   if (rgm_check_device()) return -1;

@@ -36,6 +36,14 @@ struct GemmDesc {
 // Launch on `stream`. Returns cudaSuccess or the failing status; message in *err if given.
 cudaError_t launch_gemm(const GemmDesc& d, cudaStream_t stream, std::string* err = nullptr);
 
+// 3x3 convolution (CONV_3x3, EPI_F16) whose INPUT is normalised + activated on the way into the operand stage
+// (conv_gn.cuh): d.A is the RAW tensor [n_img, H, 128, C], in_ab its GroupNorm affine [n_img][C].  Needs W == 128,
+// H even, N == 128 output features.  conv_gn_shape_ok tells whether a layer qualifies, conv_gn_supported whether the VAE
+// should use it (policy: off unless RGM_CONV_GN=1, see gemm_tc.cu).
+bool conv_gn_shape_ok(const GemmDesc& d);
+bool conv_gn_supported(const GemmDesc& d);
+cudaError_t launch_conv_gn(const GemmDesc& d, const float2* in_ab, cudaStream_t stream, std::string* err = nullptr);
+
 // number of kernels this translation unit has launched since process start (bench.py's gpu_launches claim)
 unsigned long long gemm_launch_count();
 

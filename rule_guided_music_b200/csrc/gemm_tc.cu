@@ -7,6 +7,7 @@
 #include <unordered_map>
 
 #include "api_util.h"
+#include "conv_gn.cuh"
 #include "gemm_host.h"
 
 namespace rgm {
@@ -232,6 +233,8 @@ cudaError_t launch_gemm(const GemmDesc& d, cudaStream_t stream, std::string* err
   }
   p.epi = d.e;
   p.trace = d.trace;
+  p.par_fast = 1;
+  if (const char* pf = getenv("RGM_PAR_FAST")) p.par_fast = atoi(pf);  // A/B knob: 0 = parity-major tile order
   if (const char* bn = getenv("RGM_GEMM_BAND")) p.band_n = atoi(bn);  // experiment knobs, read per launch
   if (const char* dbg = getenv("RGM_GEMM_DEBUG")) p.debug = atoi(dbg);
   if (const char* tp = getenv("RGM_DEBUG_TRACE_PTR")) {  // development aid: trace every launch with a given epilogue
@@ -331,6 +334,81 @@ cudaError_t launch_gemm(const GemmDesc& d, cudaStream_t stream, std::string* err
     }
   }
   if (st != cudaSuccess && err) *err = std::string("gemm launch: ") + cudaGetErrorString(st);
+  return st;
+}
+
+// shape test: layers the fused kernel can run
+bool conv_gn_shape_ok(const GemmDesc& d) {
+  return d.conv == CONV_3x3 && d.epi == EPI_F16 && d.W == CG_W && d.H >= 2 && d.H % CG_ROWS == 0 && d.N == SW_FEATS &&
+         d.C % GEMM_BLOCK_K == 0 && d.lda == d.C && d.b_batch <= 1 && d.e.up2 == 0 && d.e.addtab == nullptr;
+}
+
+// policy: whether the VAE uses it.  OFF by default: measured on B200 (profiles/README.md, round 2) one launch of the fused
+// kernel takes 0.93 ms at 128 -> 128 @ 128x128 against 0.57 + 0.22 ms for convolution + GroupNorm pass -- an N = 128
+// tcgen05.mma with both operands in shared memory is shared-memory-bound (107 instead of 64 cycles per 128x128x16) and
+// the in-place transform (11 K cycles per k-block on four warps) does not hide under it.  RGM_CONV_GN=1 switches it on.
+bool conv_gn_supported(const GemmDesc& d) {
+  static const int on = [] {
+    const char* e = getenv("RGM_CONV_GN");
+    return (e && atoi(e) == 1) ? 1 : 0;
+  }();
+  return on && conv_gn_shape_ok(d);
+}
+
+cudaError_t launch_conv_gn(const GemmDesc& d, const float2* in_ab, cudaStream_t stream, std::string* err) {
+  auto fail = [&](const char* m) {
+    if (err) *err = m;
+    return cudaErrorInvalidValue;
+  };
+  if (!conv_gn_shape_ok(d) || in_ab == nullptr) return fail("conv_gn: unsupported layer shape");
+  if ((reinterpret_cast<uintptr_t>(d.A) & 15) || (reinterpret_cast<uintptr_t>(d.B) & 15))
+    return fail("conv_gn: operands must be 16-byte aligned");
+  if (d.rows_b < d.N) return fail("conv_gn: weight rows");
+  GemmParams p;
+  std::memset(&p, 0, sizeof(p));
+  p.M = d.n_img * d.H * d.W;
+  p.N = d.N;
+  p.num_m_tiles = d.n_img * (d.H / CG_ROWS);
+  p.num_n_tiles = 1;
+  p.num_par = 1;
+  p.num_taps = 9;
+  p.kb_per_tap = d.C / GEMM_BLOCK_K;
+  p.slots_per_par = (p.M + 127) / 128;
+  p.in_stride = 1;
+  p.epi = d.e;
+  p.trace = d.trace;
+  if (const char* dbg = getenv("RGM_GEMM_DEBUG")) p.debug = atoi(dbg);
+  ConvGnParams cg;
+  cg.in_ab = in_ab;
+  cg.H = d.H;
+  cg.kb = d.C / GEMM_BLOCK_K;
+  CUtensorMap mx, mw;
+  {
+    cuuint64_t dims[4] = {(cuuint64_t)d.C, (cuuint64_t)d.W, (cuuint64_t)d.H, (cuuint64_t)d.n_img};
+    cuuint64_t strides[3] = {(cuuint64_t)d.lda * 2, (cuuint64_t)d.W * d.lda * 2, (cuuint64_t)d.H * d.W * d.lda * 2};
+    cuuint32_t box[4] = {GEMM_BLOCK_K, CG_HALO_W, CG_HALO_ROWS, 1};
+    if (!make_map(&mx, d.A, 4, dims, strides, box, err)) return cudaErrorInvalidValue;
+  }
+  {
+    const long long K = 9LL * d.C;
+    cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)d.rows_b, 1};
+    cuuint64_t strides[2] = {(cuuint64_t)K * 2, (cuuint64_t)K * d.rows_b * 2};
+    cuuint32_t box[3] = {GEMM_BLOCK_K, SW_FEATS, 1};
+    if (!make_map(&mw, d.B, 3, dims, strides, box, err)) return cudaErrorInvalidValue;
+  }
+  int grid = p.num_m_tiles < device_sm_count() ? p.num_m_tiles : device_sm_count();
+  if (grid <= 0) return cudaSuccess;
+  char pname[96];
+  const double fl = 2.0 * (double)p.M * d.N * 9.0 * d.C;
+  if (g_prof_on.load(std::memory_order_relaxed))
+    snprintf(pname, sizeof pname, "conv_gn conv1 H%d K%d N%d epi0 f128xr2x128 norm+swish fused", d.H, 9 * d.C, d.N);
+  ProfScope prof(pname, fl, fl, 0.0, stream);
+  static SmemAttr attr;
+  if (cudaError_t e = attr.ensure(conv_gn_kernel, CG_SMEM_BYTES); e != cudaSuccess) return e;
+  conv_gn_kernel<<<grid, CG_THREADS, CG_SMEM_BYTES, stream>>>(mx, mw, p, cg);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  cudaError_t st = cudaGetLastError();
+  if (st != cudaSuccess && err) *err = std::string("conv_gn launch: ") + cudaGetErrorString(st);
   return st;
 }
 

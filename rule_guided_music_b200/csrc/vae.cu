@@ -77,7 +77,9 @@ struct Vae {
   // of the other occupy the tcgen05 pipe (a GEMM CTA takes all shared memory of an SM but leaves registers and
   // thread slots for an elementwise block).
   struct Lane {
-    DevBuf act[4], gnpart, abbuf, attn_s;
+    // abbuf[2]: GroupNorm affines ping-pong -- a convolution reads its input's affine from one (fused normalise, or the
+    // gn_apply pass before it) while its output's affine is written into the other
+    DevBuf act[4], gnpart, abbuf[2], attn_s;
     cudaStream_t stream = nullptr;
     cudaEvent_t done = nullptr;
   } lane[2];
@@ -220,7 +222,10 @@ struct Ctx {
   Vae* m;
   Vae::Lane* L;
   cudaStream_t st;
-  int nt;  // tiles in this chunk
+  int nt;        // tiles in this chunk
+  int ab_i = 0;  // which of L->abbuf holds the affine of the tensor about to be normalised
+  float2* ab() const { return static_cast<float2*>(L->abbuf[ab_i].p); }
+  float2* ab_other() const { return static_cast<float2*>(L->abbuf[ab_i ^ 1].p); }
 };
 
 #define RGM_VGEMM_OK(desc)                                                                    \
@@ -229,8 +234,13 @@ struct Ctx {
     if (launch_gemm(desc, c.st, &_err) != cudaSuccess) return set_error("rgm_vae: " + _err);  \
   } while (0)
 
-// conv on NHWC fp16 [nt, H, H, cin] -> out [nt, H', H', cout]; optional residual; emits GroupNorm partials
-int run_conv(Ctx& c, const Conv& cv, const __half* x, int H, const __half* resid, __half* out, bool want_gn) {
+// conv on NHWC fp16 [nt, H, H, cin] -> out [nt, H', H', cout]; optional residual.  `next` = the GroupNorm that consumes
+// `out` (or null): the epilogue then emits the partial statistics of the stored tensor and a small finalize launch folds
+// them into that norm's per-(tile, channel) affine, so no statistics pass over the tensor follows.  (Folding inside the
+// epilogue -- last-arriving warp per image behind a device-scope fence -- was measured in round 2: the fences and the
+// serial fold cost 2-10x on the short-K convolutions; profiles/README.md.)
+int run_conv(Ctx& c, const Conv& cv, const __half* x, int H, const __half* resid, __half* out, const Norm* next,
+             bool fuse_input_norm = false) {
   GemmDesc d;
   d.A = x;
   d.n_img = c.nt;
@@ -249,62 +259,86 @@ int run_conv(Ctx& c, const Conv& cv, const __half* x, int H, const __half* resid
   d.e.alpha = 1.f;
   d.e.resid = resid;
   d.e.ldr = cv.cout;
-  d.e.gn_part = want_gn ? static_cast<float*>(c.L->gnpart.p) : nullptr;
   if (cv.kind == CONV_UP2) {
     d.e.up2 = 1;
     d.e.upH = H;
     d.e.upW = H;
   }
-  RGM_VGEMM_OK(d);
+  if (next != nullptr) {
+    if (next->c != cv.cout || cv.cout % 128 != 0) return set_error("rgm_vae: GroupNorm partials need a 128-multiple channel count");
+    d.e.gn_part = static_cast<float*>(c.L->gnpart.p);
+  }
+  if (fuse_input_norm) {  // x is RAW: normalise + swish with the current affine inside the operand path (conv_gn.cuh)
+    std::string err;
+    if (launch_conv_gn(d, c.ab(), c.st, &err) != cudaSuccess) return set_error("rgm_vae: " + err);
+  } else {
+    RGM_VGEMM_OK(d);
+  }
+  if (next != nullptr) {
+    // fold the epilogue's partial sums into the consumer norm's per-(tile, channel) affine, in the OTHER affine buffer
+    // (this convolution may still be reading the current one), which then becomes the current one
+    const int oH = cv.kind == CONV_DOWN2 ? H / 2 : H;  // GEMM rows are output pixels (low-res ones for UP2)
+    const int npar = cv.kind == CONV_UP2 ? 4 : 1;
+    const int low = oH * oH;
+    if (low % 128 != 0) return set_error("rgm_vae: GroupNorm partials need images of a multiple of 128 pixels");
+    RGM_CUDA_OK(launch_gn_finalize(static_cast<float*>(c.L->gnpart.p), next->gamma, next->beta, c.ab_other(), c.nt,
+                                   low / 128, npar, (long long)c.nt * low / 128, next->c, npar * low, 1e-6f, c.st));
+    c.ab_i ^= 1;
+  }
   return 0;
 }
 
-// GroupNorm affine (a, b) per (tile, channel) from the partials the last run_conv wrote
-int gn_from_part(Ctx& c, const Norm& n, int H_in, bool was_up2) {
-  const int lowHW = H_in * H_in;
-  const long long par_stride = (long long)c.nt * lowHW / 128;
-  RGM_CUDA_OK(launch_gn_finalize(static_cast<float*>(c.L->gnpart.p), n.gamma, n.beta,
-                                 static_cast<float2*>(c.L->abbuf.p), c.nt, lowHW / 128, was_up2 ? 4 : 1, par_stride, n.c,
-                                 was_up2 ? 4 * lowHW : lowHW, 1e-6f, c.st));
-  return 0;
+// whether conv(swish(norm(x))) of this layer can run as one kernel
+bool can_fuse_norm(const Ctx& c, const Conv& cv, int H) {
+  GemmDesc d;
+  d.n_img = c.nt;
+  d.H = H;
+  d.W = H;
+  d.C = cv.cin;
+  d.lda = cv.cin;
+  d.N = cv.cout;
+  d.conv = cv.kind;
+  d.epi = EPI_F16;
+  return conv_gn_supported(d);
 }
 
-// ResnetBlock (model.py:117-137). x: input [nt,H,H,cin] whose GroupNorm partials are current; t, h: scratch; out may
-// alias neither x nor h.  Leaves the partials of `out` current.
-int run_res(Ctx& c, const Res& r, const __half* x, int H, bool x_from_up2, __half* t, __half* h, __half* out,
+// ResnetBlock (model.py:117-137). x: input [nt,H,H,cin] whose GroupNorm affine (norm1) is current in L->abbuf -- its
+// producer's epilogue put it there -- unless stats_from_tensor; t, h: scratch; out may alias neither x nor h.  `next` =
+// the norm that consumes this block's output (its affine is left current), or null.
+int run_res(Ctx& c, const Res& r, const __half* x, int H, __half* t, __half* h, __half* out, const Norm* next,
             bool stats_from_tensor = false) {
   const int HW = H * H;
-  if (stats_from_tensor) {  // x did not come out of a GEMM epilogue (the stems): one direct statistics pass
-    RGM_CUDA_OK(launch_gn_stats(x, r.n1.gamma, r.n1.beta, static_cast<float2*>(c.L->abbuf.p), c.nt, HW, r.n1.c, 1e-6f,
-                                c.st));
-  } else if (gn_from_part(c, r.n1, x_from_up2 ? H / 2 : H, x_from_up2)) {
-    return -1;
+  if (stats_from_tensor)  // x did not come out of a GEMM epilogue (the stems): one direct statistics pass
+    RGM_CUDA_OK(launch_gn_stats(x, r.n1.gamma, r.n1.beta, c.ab(), c.nt, HW, r.n1.c, 1e-6f, c.st));
+  const bool f1 = can_fuse_norm(c, r.c1, H), f2 = can_fuse_norm(c, r.c2, H);
+  if (f1) {
+    if (run_conv(c, r.c1, x, H, nullptr, h, &r.n2, true)) return -1;
+  } else {
+    RGM_CUDA_OK(launch_gn_apply(x, c.ab(), t, c.nt, HW, r.n1.c, 1, c.st));
+    if (run_conv(c, r.c1, t, H, nullptr, h, &r.n2)) return -1;
   }
-  RGM_CUDA_OK(launch_gn_apply(x, static_cast<float2*>(c.L->abbuf.p), t, c.nt, HW, r.n1.c, 1, c.st));
-  if (run_conv(c, r.c1, t, H, nullptr, h, true)) return -1;
-  if (gn_from_part(c, r.n2, H, false)) return -1;
-  RGM_CUDA_OK(launch_gn_apply(h, static_cast<float2*>(c.L->abbuf.p), t, c.nt, HW, r.n2.c, 1, c.st));
+  if (!f2) RGM_CUDA_OK(launch_gn_apply(h, c.ab(), t, c.nt, HW, r.n2.c, 1, c.st));
   const __half* resid = x;
   if (r.has_nin) {
-    if (run_conv(c, r.nin, x, H, nullptr, out, false)) return -1;
+    if (run_conv(c, r.nin, x, H, nullptr, out, nullptr)) return -1;
     resid = out;  // conv2 adds the shortcut it finds in `out` and overwrites it (same thread reads then writes)
   }
-  return run_conv(c, r.c2, t, H, resid, out, true);
+  return run_conv(c, r.c2, f2 ? h : t, H, resid, out, next, f2);
 }
 
 // AttnBlock (model.py:168-192) at 16x16: single head over the 256 positions of a tile.  x = buf[cur] (its GroupNorm
 // partials current); the result x + proj_out(attention) lands in buf[0] with its partials current.  cur must be 3.
 int run_mid_attn(Ctx& c, const Norm& norm, const Conv& cq, const Conv& ck, const Conv& cvv, const Conv& cproj,
-                 __half* const* buf, int cur, int H, int C) {
+                 __half* const* buf, int cur, int H, int C, const Norm* next) {
   const int nt = c.nt;
   cudaStream_t st = c.st;
   Vae::Lane* L = c.L;
-  float2* ab = static_cast<float2*>(L->abbuf.p);
+  float2* ab = c.ab();
   const int HW = H * H;
   __half* x = buf[cur];
   __half* hn = buf[0];
-  if (gn_from_part(c, norm, H, false)) return -1;
-  RGM_CUDA_OK(launch_gn_apply(x, ab, hn, nt, HW, C, 0, st));
+  if (norm.c != C) return set_error("rgm_vae: attention norm width");
+  RGM_CUDA_OK(launch_gn_apply(x, ab, hn, nt, HW, C, 0, st));  // the affine of `norm` is current (producer's epilogue)
   // q, k, v, v^T, P carve buf[1] and buf[2] (each holds >= 4 tensors of this size: buffers are sized for 128x128x256)
   const long long tsz = (long long)nt * HW * C;
   __half* q = buf[1];
@@ -313,9 +347,9 @@ int run_mid_attn(Ctx& c, const Norm& norm, const Conv& cq, const Conv& ck, const
   __half* vT = buf[2];
   __half* P = buf[2] + tsz;
   __half* ao = buf[2] + 2 * tsz;
-  if (run_conv(c, cq, hn, H, nullptr, q, false)) return -1;
-  if (run_conv(c, ck, hn, H, nullptr, k, false)) return -1;
-  if (run_conv(c, cvv, hn, H, nullptr, v, false)) return -1;
+  if (run_conv(c, cq, hn, H, nullptr, q, nullptr)) return -1;
+  if (run_conv(c, ck, hn, H, nullptr, k, nullptr)) return -1;
+  if (run_conv(c, cvv, hn, H, nullptr, v, nullptr)) return -1;
   RGM_CUDA_OK(launch_transpose(v, vT, nt, HW, C, st));
   float* S = static_cast<float*>(L->attn_s.p);
   {
@@ -357,7 +391,7 @@ int run_mid_attn(Ctx& c, const Norm& norm, const Conv& cq, const Conv& ck, const
     d.e.alpha = 1.f;
     RGM_VGEMM_OK(d);
   }
-  return run_conv(c, cproj, ao, H, x, hn, true);  // x + proj_out(attention)
+  return run_conv(c, cproj, ao, H, x, hn, next);  // x + proj_out(attention)
 }
 
 int decode_chunk(Vae* m, Vae::Lane* L, const float* lat, float scale, float* roll, int n_cand, int Hlat, int roll_ch,
@@ -365,53 +399,43 @@ int decode_chunk(Vae* m, Vae::Lane* L, const float* lat, float scale, float* rol
   Ctx c{m, L, st, nt};
   __half* buf[4];
   for (int i = 0; i < 4; ++i) buf[i] = static_cast<__half*>(L->act[i].p);
-  float2* ab = static_cast<float2*>(L->abbuf.p);
   int H = 16;
   int C = m->block_in0;
   // stem
   RGM_CUDA_OK(launch_vae_stem(lat, scale, m->pq_w, m->pq_b, m->cin_w, m->cin_b, buf[0], n_cand, Hlat, tile0, nt, C,
                               st));
   // mid.block_1: the stem has no GEMM epilogue, so its GroupNorm statistics come from a direct pass
-  {
-    const Res& r = m->mid1;
-    RGM_CUDA_OK(launch_gn_stats(buf[0], r.n1.gamma, r.n1.beta, ab, nt, H * H, C, 1e-6f, st));
-    RGM_CUDA_OK(launch_gn_apply(buf[0], ab, buf[1], nt, H * H, C, 1, st));
-    if (run_conv(c, r.c1, buf[1], H, nullptr, buf[2], true)) return -1;
-    if (gn_from_part(c, r.n2, H, false)) return -1;
-    RGM_CUDA_OK(launch_gn_apply(buf[2], ab, buf[1], nt, H * H, C, 1, st));
-    if (run_conv(c, r.c2, buf[1], H, buf[0], buf[3], true)) return -1;
-  }
+  if (run_res(c, m->mid1, buf[0], H, buf[1], buf[2], buf[3], &m->attn_norm, /*stats_from_tensor=*/true)) return -1;
   int cur = 3;  // buf[cur] holds x
   // mid.attn_1 (model.py:168-192)
-  if (run_mid_attn(c, m->attn_norm, m->attn_q, m->attn_k, m->attn_v, m->attn_proj, buf, cur, H, C)) return -1;
+  if (run_mid_attn(c, m->attn_norm, m->attn_q, m->attn_k, m->attn_v, m->attn_proj, buf, cur, H, C, &m->mid2.n1)) return -1;
   cur = 0;
   // mid.block_2
   {
     const int o = (cur + 3) & 3;
-    if (run_res(c, m->mid2, buf[cur], H, false, buf[(cur + 1) & 3], buf[(cur + 2) & 3], buf[o])) return -1;
+    if (run_res(c, m->mid2, buf[cur], H, buf[(cur + 1) & 3], buf[(cur + 2) & 3], buf[o], &m->up[m->n_levels - 1][0].n1))
+      return -1;
     cur = o;
   }
-  bool from_up = false;
   for (int lvl = m->n_levels - 1; lvl >= 0; --lvl) {
     for (int b = 0; b <= m->nres; ++b) {
       const int o = (cur + 3) & 3;
-      if (run_res(c, m->up[lvl][b], buf[cur], H, from_up, buf[(cur + 1) & 3], buf[(cur + 2) & 3], buf[o])) return -1;
+      // who normalises this block's output: the next block, norm_out after the last one, nobody before an upsample conv
+      const Norm* next = b < m->nres ? &m->up[lvl][b + 1].n1 : (lvl == 0 ? &m->norm_out : nullptr);
+      if (run_res(c, m->up[lvl][b], buf[cur], H, buf[(cur + 1) & 3], buf[(cur + 2) & 3], buf[o], next)) return -1;
       cur = o;
-      from_up = false;
     }
     if (lvl != 0) {
       const int o = (cur + 1) & 3;
-      if (run_conv(c, m->upsample[lvl], buf[cur], H, nullptr, buf[o], true)) return -1;
+      if (run_conv(c, m->upsample[lvl], buf[cur], H, nullptr, buf[o], &m->up[lvl - 1][0].n1)) return -1;
       cur = o;
       H *= 2;
-      from_up = true;
     }
   }
   // norm_out + swish + conv_out, assembled into the roll: one fused CUDA-core kernel (aux_kernels.cu)
   {
-    if (gn_from_part(c, m->norm_out, from_up ? H / 2 : H, from_up)) return -1;
     if (H != 128) return set_error("rgm_vae: decoder output is not 128x128 (the roll kernels assume 128x128 tiles)");
-    RGM_CUDA_OK(launch_vae_out(buf[cur], ab, m->cout_w, m->cout_b, roll, nt, m->norm_out.c, m->out_ch, tile0, n_cand,
+    RGM_CUDA_OK(launch_vae_out(buf[cur], c.ab(), m->cout_w, m->cout_b, roll, nt, m->norm_out.c, m->out_ch, tile0, n_cand,
                                8 * Hlat, roll_ch, st));
   }
   return 0;
@@ -423,22 +447,24 @@ int encode_chunk(Vae* m, Vae::Lane* L, const float* x, float* moments, int t0, i
   Ctx c{m, L, st, nt};
   __half* buf[4];
   for (int i = 0; i < 4; ++i) buf[i] = static_cast<__half*>(L->act[i].p);
-  float2* ab = static_cast<float2*>(L->abbuf.p);
   int H = 128;
   RGM_CUDA_OK(launch_vae_enc_stem(x + (long long)t0 * m->in_ch * 128 * 128, m->e_cin_w, m->e_cin_b, buf[0], nt, m->in_ch,
                                   m->ch, st));
   int cur = 0;
   bool first = true;
   for (int lvl = 0; lvl < m->n_levels; ++lvl) {
+    const bool last_lvl = lvl == m->n_levels - 1;
     for (int b = 0; b < m->nres; ++b) {
       const int o = (cur + 3) & 3;
-      if (run_res(c, m->down[lvl][b], buf[cur], H, false, buf[(cur + 1) & 3], buf[(cur + 2) & 3], buf[o], first)) return -1;
+      // who normalises this block's output: the next block, mid.block_1 after the last level, nobody before a Downsample
+      const Norm* next = b < m->nres - 1 ? &m->down[lvl][b + 1].n1 : (last_lvl ? &m->e_mid1.n1 : nullptr);
+      if (run_res(c, m->down[lvl][b], buf[cur], H, buf[(cur + 1) & 3], buf[(cur + 2) & 3], buf[o], next, first)) return -1;
       cur = o;
       first = false;
     }
-    if (lvl != m->n_levels - 1) {
+    if (!last_lvl) {
       const int o = (cur + 1) & 3;
-      if (run_conv(c, m->downsample[lvl], buf[cur], H, nullptr, buf[o], true)) return -1;  // stride 2: H -> H/2
+      if (run_conv(c, m->downsample[lvl], buf[cur], H, nullptr, buf[o], &m->down[lvl + 1][0].n1)) return -1;  // H -> H/2
       cur = o;
       H /= 2;
     }
@@ -449,27 +475,28 @@ int encode_chunk(Vae* m, Vae::Lane* L, const float* x, float* moments, int t0, i
     const int o = 3;  // run_mid_attn wants its input in buf[3]
     if (cur == o) {   // (with 4 levels x 2 blocks + 3 downsamples cur is 3 here only by accident of the ping-pong)
       const int o2 = (cur + 3) & 3;
-      if (run_res(c, m->e_mid1, buf[cur], H, false, buf[(cur + 1) & 3], buf[(cur + 2) & 3], buf[o2])) return -1;
+      if (run_res(c, m->e_mid1, buf[cur], H, buf[(cur + 1) & 3], buf[(cur + 2) & 3], buf[o2], &m->e_attn_norm)) return -1;
       RGM_CUDA_OK(cudaMemcpyAsync(buf[o], buf[o2], (size_t)nt * H * H * C * sizeof(__half), cudaMemcpyDeviceToDevice, st));
     } else {
       int t1 = -1, t2 = -1;  // two scratch buffers that are neither cur nor 3
       for (int i = 0; i < 3; ++i)
         if (i != cur) (t1 < 0 ? t1 : t2) = i;
-      if (run_res(c, m->e_mid1, buf[cur], H, false, buf[t1], buf[t2], buf[o])) return -1;
+      if (run_res(c, m->e_mid1, buf[cur], H, buf[t1], buf[t2], buf[o], &m->e_attn_norm)) return -1;
     }
     cur = o;
   }
-  if (run_mid_attn(c, m->e_attn_norm, m->e_attn_q, m->e_attn_k, m->e_attn_v, m->e_attn_proj, buf, cur, H, C)) return -1;
+  if (run_mid_attn(c, m->e_attn_norm, m->e_attn_q, m->e_attn_k, m->e_attn_v, m->e_attn_proj, buf, cur, H, C,
+                   &m->e_mid2.n1))
+    return -1;
   cur = 0;
   {
     const int o = (cur + 3) & 3;
-    if (run_res(c, m->e_mid2, buf[cur], H, false, buf[(cur + 1) & 3], buf[(cur + 2) & 3], buf[o])) return -1;
+    if (run_res(c, m->e_mid2, buf[cur], H, buf[(cur + 1) & 3], buf[(cur + 2) & 3], buf[o], &m->e_norm_out)) return -1;
     cur = o;
   }
   // norm_out + swish, conv_out (C -> 2*zc, fp32 out, feature dim padded to 32), quant_conv 1x1 -> NCHW moments
-  if (gn_from_part(c, m->e_norm_out, H, false)) return -1;
   __half* t = buf[(cur + 1) & 3];
-  RGM_CUDA_OK(launch_gn_apply(buf[cur], ab, t, nt, H * H, C, 1, st));
+  RGM_CUDA_OK(launch_gn_apply(buf[cur], c.ab(), t, nt, H * H, C, 1, st));
   float* h32 = static_cast<float*>(L->attn_s.p);
   {
     const Conv& cv = m->e_cout;
@@ -517,7 +544,7 @@ int vae_reserve(Vae* m, int chunk, int lanes, cudaStream_t st) {
     Vae::Lane& L = m->lane[l];
     for (int i = 0; i < 4; ++i) RGM_CUDA_OK(L.act[i].reserve((size_t)chunk * maxc * sizeof(__half), st));
     RGM_CUDA_OK(L.gnpart.reserve((size_t)chunk * maxc / 8 + 1024, st));
-    RGM_CUDA_OK(L.abbuf.reserve((size_t)chunk * 512 * sizeof(float2) * 2, st));
+    for (int i = 0; i < 2; ++i) RGM_CUDA_OK(L.abbuf[i].reserve((size_t)chunk * 512 * sizeof(float2) * 2, st));
     RGM_CUDA_OK(L.attn_s.reserve((size_t)chunk * 256 * 256 * sizeof(float), st));
   }
   return 0;

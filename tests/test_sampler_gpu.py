@@ -2,9 +2,12 @@
 UNMODIFIED reference produced on the CPU (tests/golden/sampler.npz).  A noise tape feeds the CUDA path the same
 Gaussian noise, in the same order, as the reference consumed; every intermediate x_t is compared.
 
-Tolerance: 1e-3 relative (BASELINE.json) per step would be the bar for one denoiser call; over a 4-6 step trajectory
-errors compound through x0-prediction (1/sqrt(alpha_bar) up to ~160 at t = 999 for the first step), so the bar here is
-1e-2 relative L2 per step against the fp32 reference, plus bit-exact selection checks in test_rules_gpu.py."""
+Tolerance: 1e-3 relative (BASELINE.json) is the bar for one teacher-forced step of the flagship configuration
+(tests/test_flagship_gpu.py).  These are FREE-RUNNING 4-6 step trajectories that span the whole schedule (each step
+covers 170-250 original timesteps), so errors compound through x0-prediction (1/sqrt(alpha_bar) up to ~160 at t = 999);
+the bar is 3e-3 relative L2 per step against the fp32 reference (measured on B200: <= 1.25e-3), plus bit-exact
+selection checks in test_rules_gpu.py."""
+TRAJ_TOL = 3e-3
 import os
 from functools import partial
 from types import SimpleNamespace
@@ -47,5 +50,5 @@ def test_trajectory_matches_reference(cuda, tag, parity):
     assert len(steps) == ref.shape[0]
     errs = [gpu_util.rel_l2(s, r) for s, r in zip(steps, ref)]
     for i, e in enumerate(errs):
-        parity(f"free-running trajectory {tag}, x_t after step {i}", e, 1e-2)
-    assert max(errs) < 1e-2, errs
+        parity(f"free-running trajectory {tag}, x_t after step {i}", e, TRAJ_TOL)
+    assert max(errs) < TRAJ_TOL, errs

@@ -4,7 +4,8 @@ evaluated by the warp-shuffle reduction kernels of csrc/rules.cu.
 Signatures and results follow the reference: ``f(piano_roll [B,3,128,L] in [-1,1]) -> [B,K]`` (squeezed to ``[K]``
 when B == 1), and -- like the reference -- channel 0 of the input is modified IN PLACE (piano mask, -0.95
 threshold), so the order in which rules run matters.  CUDA tensors only; there is no CPU path here.
-The chord rules (music21) are not implemented: their parity cannot be pinned offline.
+The chord rule (`get_chords`) is a host rule in chords.py: the reference's own parts are restated and pinned, the music21
+analysis is a pluggable analyzer (docs/CHORD_SPEC.md).
 """
 import torch
 
@@ -77,7 +78,4 @@ def note_density_class(piano_roll, interval=128, quantize_factor=1, horizontal_s
                      dim=-1)
 
 
-def get_chords(*a, **k):
-    raise NotImplementedError(
-        "chord_progression needs music21 (not vendored by the reference, not installable offline): parity unpinned, "
-        "not implemented on the B200 path; register your own callable in FUNC_DICT to use it")
+from .chords import get_chords  # noqa: E402,F401  (host rule: music_rules.py:97-130, see chords.py)

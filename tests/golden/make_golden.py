@@ -394,8 +394,46 @@ def golden_flagship():
         gd.FUNC_DICT["pitch_hist"], gd.LOSS_DICT["pitch_hist"] = real_func, real_loss
     save("flagship", **out)
 
+def golden_chords():
+    """The reference-owned parts of the chord rule (docs/CHORD_SPEC.md parts 1 and 3): the integer roll get_chords hands
+    to piano_roll_to_chords, the note list piano_roll_to_pretty_midi extracts from it, the window vote and the degree
+    tags.  music21 itself (part 2) is not available here: piano_roll_to_chords is intercepted at its entry."""
+    import music_rule_guidance.music_rules as rmr
+    import music_rule_guidance.piano_roll_to_chord as rch
+
+    out = {}
+    captured = []
+
+    def fake_p2c(piano_roll, given_key=None, fs=100, window_size=1.28, return_key=False):
+        captured.append(np.array(piano_roll, copy=True))
+        return {"chords": torch.zeros(int(piano_roll.shape[-1] / fs / window_size), dtype=torch.long)}
+
+    real = rmr.piano_roll_to_chords
+    rmr.piano_roll_to_chords = fake_p2c
+    try:
+        roll = gi.chord_rolls()
+        keep = roll.clone()
+        res = rmr.get_chords(roll)
+        out["velocities"] = np.stack(captured)
+        out["get_chords_shape"] = np.array(res.shape)
+        out["roll_after_ch0_sub"] = roll[:, 0, ::8, ::16].numpy()       # the in-place mask / threshold side effect
+        out["roll_changed"] = int(not torch.equal(roll, keep))
+    finally:
+        rmr.piano_roll_to_chords = real
+    for i, v in enumerate(out["velocities"]):
+        pm = rch.piano_roll_to_pretty_midi(v.copy(), fs=100)
+        notes = [(n.pitch, n.start, n.end, n.velocity) for n in pm.instruments[0].notes]
+        out[f"notes_{i}"] = np.array(notes, dtype=np.float64).reshape(-1, 4)
+    pm = rch.piano_roll_to_pretty_midi(out["velocities"][0][:, :160].copy(), fs=12.5)
+    out["notes_fs12"] = np.array([(n.pitch, n.start, n.end, n.velocity) for n in pm.instruments[0].notes],
+                                 dtype=np.float64).reshape(-1, 4)
+    for tag, (chords, end_time, win, total) in gi.chord_vote_cases().items():
+        out["vote_" + tag] = np.array(rch.get_longest_chords(chords, end_time, window_size=win, total_time=total))
+    out["tags"] = np.array([rch.chord_tag_num(f) for f in gi.CHORD_FIGURES])
+    save("chords", **out)
+
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["schedule", "rules", "dit", "vae", "vae_enc", "collage", "host", "sampler", "sampler_ext", "flagship"]
+    which = sys.argv[1:] or ["schedule", "rules", "dit", "vae", "vae_enc", "collage", "host", "sampler", "sampler_ext", "flagship", "chords"]
     for w in which:
         globals()["golden_" + w]()

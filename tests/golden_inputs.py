@@ -287,3 +287,49 @@ def flagship_inputs(case, alphas_cumprod):
     ab = float(alphas_cumprod[c["t_index"]])
     x_t = ab ** 0.5 * x0 + (1 - ab) ** 0.5 * torch.randn(1, 4, 128, 16, generator=g)
     return x_t.float(), torch.tensor([c["t_index"]], dtype=torch.long)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# chord rule, reference-owned parts (docs/CHORD_SPEC.md): goldens in tests/golden/chords.npz
+# ---------------------------------------------------------------------------------------------------------------
+def chord_rolls(B=3, L=1024):
+    """Rolls with held chords, repeated notes, overlapping voices, a note running to the last frame, out-of-range pitches,
+    values around the -0.95 threshold, and low-level 'background' noise in the out-of-range rows."""
+    g = torch.Generator(device="cpu").manual_seed(91)
+    r = -torch.ones(B, 3, 128, L)
+    for b in range(B):
+        t = 0
+        while t < L - 40:
+            d = int(torch.randint(20, 160, (1,), generator=g))
+            root = int(torch.randint(40, 80, (1,), generator=g))
+            for iv in (0, 4, 7) if b != 1 else (0, 3, 7, 10):
+                v = float(torch.rand(1, generator=g)) * 1.4 - 0.5
+                r[b, 0, root + iv, t:min(t + d, L)] = v
+            t += d + int(torch.randint(0, 12, (1,), generator=g))
+    r[0, 0, 60, L - 30:] = 0.9            # still sounding at the end
+    r[1, 0, 10, :] = 0.5                  # below the piano range: masked
+    r[1, 0, 115, 100:200] = 0.5           # above
+    r[2, 0, 64, 300:340] = -0.95          # exactly the threshold: kept (velocity 3)
+    r[2, 0, 65, 300:340] = -0.951         # below: removed
+    r[2, 0, 66, 400:401] = 1.3            # beyond the range: clamped to 127, one frame long
+    return r + 0.0 * torch.randn(B, 3, 128, L, generator=g)
+
+
+CHORD_FIGURES = ["I", "i6", "V7", "v", "IV64", "iv", "vii/o7", "VII", "VI", "vi6", "iii+64", "#iii6b42", "II", "bII6",
+                 "ii/o42", "null", "N6", "Ger65", "It6", "Fr43", "V/V", "viio7/V", "", "IV/vi"]
+
+
+def chord_vote_cases():
+    """(chords [[duration, offset, figure]], end_time, window, total_time) for get_longest_chords."""
+    g = torch.Generator(device="cpu").manual_seed(92)
+    out = {}
+    for k, (win, total) in enumerate(((1.28, 10.24), (1.6, 10.24), (1.28, 5.12))):
+        chords, t = [], 0.0
+        while t < total * 0.9:
+            d = float(torch.rand(1, generator=g)) * 2.0 + 0.05
+            fig = CHORD_FIGURES[int(torch.randint(0, 15, (1,), generator=g))]
+            chords.append([d, t, fig])
+            t += d + (0.7 if k == 1 and len(chords) % 3 == 0 else 0.0)   # gaps -> 'null' windows
+        out[f"case{k}"] = (chords, min(t, total), win, total)
+    out["short"] = ([[0.5, 0.0, "I"], [0.3, 0.5, "V"]], 0.8, 1.28, 10.24)   # music ends early: padded with 'null'
+    return out

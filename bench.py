@@ -569,8 +569,16 @@ def run_b200(args):
                            ms / args.steps}, f, indent=1)
         print(json.dumps(line), flush=True)
     if world > 1:
+        import gc
+
         import torch.distributed as dist
 
+        # captured graphs that contain NCCL kernels must be gone before the communicator is torn down (destroying the
+        # process group with such a graph alive blocks in ncclCommDestroy)
+        wl.diffusion.enable_cuda_graphs(False)
+        del wl
+        gc.collect()
+        torch.cuda.synchronize()
         dist.barrier()
         dist.destroy_process_group()
 

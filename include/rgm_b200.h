@@ -62,7 +62,7 @@ int rgm_dit_reserve(rgm_dit* h, int B, int H);
 int rgm_dit_load(rgm_dit* h, const char* key, const float* src, long long numel, void* stream);
 /* model(x, t, y) (dit.py:618-634): x f32 [B, C, H, latent_w]; t f32 [B] (already mapped / rescaled by the caller,
  * respace.py:123-128); y int64 [B] label rows or NULL (dit.py:627-629); out f32 [B, C_out, H, latent_w].
- * H * latent_w / patch must be 128 or 256 tokens. */
+ * H * latent_w / patch must be 64, 128, 192 or 256 tokens. */
 int rgm_dit_forward(rgm_dit* h, const float* x, const float* t, const long long* y, float* out, int B, int H,
                     void* stream);
 
@@ -202,7 +202,7 @@ int rgm_conv_gn_f16(const void* x16_raw, const float* ab_in, const void* w16_pac
 int rgm_pack_conv_weight(const float* w32, void* w16_packed, int Cout, int Cin, int cout_pad, int cin_pad, int kind,
                          void* stream);
 /* softmax(q k^T * scale) v per (sample, head) (dit.py:274-277): q,k fp16 [B,heads,T,dh], vt fp16 [B,heads,dh,T],
- * out fp16 [B*T, heads*dh]; T in {128, 256} */
+ * out fp16 [B*T, heads*dh]; T in {64, 128, 192, 256} */
 int rgm_attention_f16(const void* q16, const void* k16, const void* vt16, void* out16, int B, int heads, int T, int dh,
                       float scale, void* stream);
 

@@ -13,6 +13,7 @@
 // one warp per scheduler the softmax was a chain of exposed tcgen05.ld / MUFU / st.shared latencies (49 ms per step
 // against an 11 ms MUFU floor); two warps per scheduler overlap each other's latencies and halve the per-warp work.
 #include <atomic>
+#include <cstdlib>
 #include <mutex>
 #include <unordered_map>
 
@@ -37,9 +38,14 @@ struct AttnParams {
   int nkb;       // 64-wide k-blocks of the head dimension (1 or 2)
   int ksteps;    // ceil(dh / 16) MMA K steps for S
   int npv;       // dh rounded up to 16: N of the P V MMA
-  int n_tiles;   // T / 128
+  int n_tiles;   // ceil(T / 128) query tiles; T is a multiple of 64 (the last tile may be half full)
   float scale_log2e;
   __half* out;   // [B*T, heads*dh]
+  // development aid: CTA 0 writes clock64() at pipeline events of each of its pairs, 16 slots per pair
+  // (tools/gpu_trace_attention.py): MMA thread 0 pair start (TMEM free), 1 operands A landed, 2 S tiles issued,
+  // 3 P0 seen, 4 PV0 issued, 5 P1 seen, 6 PV1 issued; softmax warp 1: 8 S0 ready, 9 max pass 0 done, 10 P0 written,
+  // 11 S1 ready, 12 P1 written, 13 O0 ready, 14 epilogue done
+  unsigned long long* trace;
 };
 
 __device__ __forceinline__ float ex2(float x) {
@@ -65,7 +71,9 @@ attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int T = p.T;
   const uint32_t q_bytes = p.nkb * 16384u;           // per query tile: nkb blocks of [128 rows][128 B]
-  const uint32_t k_blk = (uint32_t)T * 128u;         // one k-block of K: [T rows][128 B]
+  // one k-block of K: [n_tiles * 128 rows][128 B] -- K arrives in 128-row boxes, so the buffer holds whole boxes; rows
+  // past T (the next pair's, or zero fill at the end of the tensor) are never read: the S MMA has N = T
+  const uint32_t k_blk = (uint32_t)p.n_tiles * 16384u;
   const uint32_t v_blk = (uint32_t)p.npv * 128u;     // one 64-token block of V^T: [npv rows][128 B]
   uint8_t* sQ = smem;                                // query tile 0 (tile 1 is staged in the P buffer, see below)
   uint8_t* sK = sQ + q_bytes;
@@ -137,6 +145,9 @@ attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
   }
 
   uint32_t it = 0;
+  const bool tracing = p.trace != nullptr && blockIdx.x == 0;
+#define ATT_TRACE(slot) \
+  if (tracing) p.trace[it * 16 + (slot)] = clock64()
   for (int pair = blockIdx.x; pair < p.n_pairs; pair += gridDim.x, ++it) {
     const uint32_t ph = it & 1;
     if (warp == 0) {
@@ -145,8 +156,10 @@ attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
         const int next = pair + gridDim.x;
         if (it > 0) mbar_wait(bar_done, ph ^ 1);
         tc_fence_after();
+        ATT_TRACE(0);
         mbar_wait(bar_load, ph);
         tc_fence_after();
+        ATT_TRACE(1);
         // S tiles (tile 1 needs Q1 from group B)
         for (int m = 0; m < p.n_tiles; ++m) {
           if (m == 1) {
@@ -160,6 +173,7 @@ attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
           }
           umma_commit(&bar_s[m]);
         }
+        ATT_TRACE(2);
         // Q0 and K have been read once the last S tile is complete: prefetch the next pair's
         if (next < p.n_pairs) {
           mbar_wait(&bar_s[p.n_tiles - 1], ph);
@@ -173,12 +187,14 @@ attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
         for (int m = 0; m < p.n_tiles; ++m) {
           mbar_wait(&bar_p[m], ph);
           tc_fence_after();
+          ATT_TRACE(3 + 2 * m);
           for (int ks = 0; ks < T / 16; ++ks) {
             const int tb = ks >> 2, kk = ks & 3;
             umma_f16(tmem_base + m * 256, umma_desc_sw128(sP + tb * 16384) + 2 * kk,
                      umma_desc_sw128(sV + tb * v_blk) + 2 * kk, idesc_o, ks != 0);
           }
           umma_commit(&bar_o[m]);
+          ATT_TRACE(4 + 2 * m);
         }
         // the P buffer (where Q1 is staged) and V^T are free once the last P V tile is complete
         if (next < p.n_pairs) {
@@ -199,6 +215,7 @@ attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
         if (m >= p.n_tiles) break;
         mbar_wait(&bar_s[m], ph);
         tc_fence_after();
+        if (threadIdx.x == 32) ATT_TRACE(8 + 3 * m);
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + m * 256;
         float mx = -INFINITY;
         for (int c = c_lo; c < c_lo + cw; c += 32) {
@@ -215,6 +232,7 @@ attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
         // the single P buffer is read by the previous tile's P V MMAs: wait for them before overwriting it
         if (m > 0) mbar_wait(&bar_o[m - 1], ph);
         else if (p.n_tiles > 1) mbar_wait(&bar_s[1], ph);  // Q1 is staged in the P buffer until S1 is done
+        if (threadIdx.x == 32 && m == 0) ATT_TRACE(9);
         const float mneg = -mx * p.scale_log2e;
         float sum = 0.f;
         for (int c = c_lo; c < c_lo + cw; c += 32) {
@@ -240,6 +258,7 @@ attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
         tc_fence_before();
         fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
         mbar_arrive(&bar_p[m]);
+        if (threadIdx.x == 32) ATT_TRACE(10 + 2 * m);
         named_bar_sync(1 + quad, 64);
         inv_sum[m] = 1.0f / (sum + red[(half ^ 1) * 128 + r]);
         named_bar_sync(1 + quad, 64);  // both sums read before the next tile's maxima overwrite the slots
@@ -251,12 +270,15 @@ attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
         if (m >= p.n_tiles) break;
         mbar_wait(&bar_o[m], ph);
         tc_fence_after();
+        if (threadIdx.x == 32 && m == 0) ATT_TRACE(13);
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + m * 256;
         __half* orow = p.out + ((long long)b * T + m * 128 + r) * (p.heads * p.dh) + head * p.dh;
+        const bool row_ok = m * 128 + r < T;  // T = 64 or 192: the last query tile is half full
         for (int c = half * 16; c < p.npv; c += 32) {
           uint32_t v[16];
           tmem_ld_32x16(taddr + c, v);
           tmem_ld_wait();
+          if (!row_ok) continue;
           uint4 pk[2];
           __half2* h2 = reinterpret_cast<__half2*>(pk);
 #pragma unroll
@@ -268,8 +290,10 @@ attention_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
       }
       tc_fence_before();
       mbar_arrive(bar_done);
+      if (threadIdx.x == 32) ATT_TRACE(14);
     }
   }
+#undef ATT_TRACE
 
   tc_fence_before();
   __syncthreads();
@@ -321,7 +345,7 @@ cudaError_t launch_attention(const __half* q, const __half* k, const __half* vt,
     if (err) *err = m;
     return cudaErrorInvalidValue;
   };
-  if (T != 128 && T != 256) return fail("attention: T must be 128 or 256 tokens");
+  if (T < 64 || T > 256 || T % 64 != 0) return fail("attention: T must be 64, 128, 192 or 256 tokens");
   if (dh % 8 != 0 || dh > 128 || dh < 16) return fail("attention: head_dim must be a multiple of 8 in [16, 128]");
   AttnParams p;
   p.n_pairs = B * heads;
@@ -331,16 +355,20 @@ cudaError_t launch_attention(const __half* q, const __half* k, const __half* vt,
   p.nkb = (dh + 63) / 64;
   p.ksteps = (dh + 15) / 16;
   p.npv = ((dh + 15) / 16) * 16;
-  p.n_tiles = T / 128;
+  p.n_tiles = (T + 127) / 128;
   p.scale_log2e = scale * 1.4426950408889634f;
   p.out = out;
+  p.trace = nullptr;
+  if (const char* tp = getenv("RGM_DEBUG_TRACE_PTR")) p.trace = reinterpret_cast<unsigned long long*>(strtoull(tp, nullptr, 0));
   CUtensorMap mq, mk, mv;
   const unsigned long long rows = (unsigned long long)B * heads * T;
   if (!map2d(&mq, q, dh, rows, 64, 128) || !map2d(&mk, k, dh, rows, 64, 128) ||
       !map2d(&mv, vt, T, (unsigned long long)B * heads * dh, 64, p.npv))
     return fail("attention: cuTensorMapEncodeTiled failed");
-  const size_t smem = 1024 + p.nkb * 16384 + (size_t)p.nkb * T * 128 + (size_t)(T / 64) * p.npv * 128 +
-                      (size_t)(T / 64) * 16384 + 128 + 2 * 128 * sizeof(float);  // (barriers + slots: 96 B of the 128)
+  const size_t p_bytes = (size_t)(T / 64) * 16384 > (size_t)(p.n_tiles - 1) * p.nkb * 16384
+                             ? (size_t)(T / 64) * 16384 : (size_t)p.nkb * 16384;  // P blocks; query tile 1 is staged there
+  const size_t smem = 1024 + p.nkb * 16384 + (size_t)p.nkb * p.n_tiles * 16384 + (size_t)(T / 64) * p.npv * 128 + p_bytes +
+                      128 + 2 * 128 * sizeof(float);  // (barriers + slots: 96 B of the 128)
   static SmemAttr attr;
   if (cudaError_t e = attr.ensure(attention_kernel, smem); e != cudaSuccess) {
     if (err) *err = std::string("attention: cudaFuncSetAttribute(shared memory): ") + cudaGetErrorString(e);

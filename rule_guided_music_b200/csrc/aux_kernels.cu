@@ -658,103 +658,135 @@ __device__ __forceinline__ void mma_16816(float (&c)[4], uint32_t a0, uint32_t a
       : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
 
-__global__ void __launch_bounds__(512) vae_out_kernel(const __half* __restrict__ x, const float2* __restrict__ ab,
-                                                      const float* __restrict__ w, const float* __restrict__ bias,
-                                                      float* __restrict__ roll, int C, int out_ch, int tile0, int n_cand,
-                                                      int roll_len, int roll_ch) {
+// B fragments of mma.m16n8k16 for the conv_out weights (col-major k16 x n8): entry [tap][kc][lane] holds
+// W[k = kc*16 + 2*(lane%4) + {0,1}][n = lane/4] and the same at k + 8 as two half2; output channels >= out_ch are zero
+// padding.  Packed ONCE when the weights are loaded (it used to be rebuilt by each of the 8192 blocks of a launch).
+__global__ void vae_out_pack_kernel(const float* __restrict__ w, uint2* __restrict__ bfrag, int C, int out_ch) {
+  const int kchunks = C >> 4;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 9 * kchunks * 32) return;
+  const int l = i & 31, kc = (i >> 5) % kchunks, tap = i / (32 * kchunks);
+  const int n = l >> 2, k0 = kc * 16 + 2 * (l & 3);
+  float v[4] = {0.f, 0.f, 0.f, 0.f};
+  if (n < out_ch) {
+    const float* wp = w + (long long)n * C * 9 + tap;
+    v[0] = wp[(k0) * 9];
+    v[1] = wp[(k0 + 1) * 9];
+    v[2] = wp[(k0 + 8) * 9];
+    v[3] = wp[(k0 + 9) * 9];
+  }
+  __half2 lo = __floats2half2_rn(v[0], v[1]), hi = __floats2half2_rn(v[2], v[3]);
+  bfrag[i] = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+}
+
+cudaError_t launch_vae_out_pack(const float* w, void* bfrag, int C, int out_ch, cudaStream_t s) {
+  if (C % 16 != 0 || out_ch < 1 || out_ch > 8) return cudaErrorInvalidValue;
+  const int n = 9 * (C / 16) * 32;
+  vae_out_pack_kernel<<<(n + 255) / 256, 256, 0, s>>>(w, static_cast<uint2*>(bfrag), C, out_ch);
+  return done();
+}
+
+__device__ __forceinline__ void cp_async_16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+}
+
+// The input channels are processed in SLICES of 64 (one 18x18x64 halo = 46 KB + 9 KB of weight fragments per block):
+// four blocks fit an SM, so one block's loads and tensor-core contraction overlap the others' MUFU-bound activation
+// (with the whole 128-channel halo resident only two blocks fit and the phases of a block ran back to back).
+constexpr int VO_SLICE = 64;
+constexpr int VO_PSTRIDE = VO_SLICE * 2 + 16;           // bytes per halo pixel: 16 B of padding -> conflict-free ldmatrix
+constexpr int VO_HALO_BYTES = 18 * 18 * VO_PSTRIDE;     // 46 656
+constexpr int VO_KC = VO_SLICE / 16;                    // k-steps per slice
+constexpr int VO_BFRAG_BYTES = 9 * VO_KC * 32 * 8;      // 9 216
+
+__global__ void __launch_bounds__(512, 4) vae_out_kernel(const __half* __restrict__ x, const float2* __restrict__ ab,
+                                                         const uint2* __restrict__ bfrag_g, const float* __restrict__ bias,
+                                                         float* __restrict__ roll, int C, int out_ch, int tile0,
+                                                         int n_cand, int roll_len, int roll_ch) {
   extern __shared__ __align__(16) uint8_t osm[];
-  const int pstride = C * 2 + 16;                       // bytes per halo pixel
-  uint8_t* halo = osm;                                  // [18*18][pstride]
-  const int kchunks = C >> 4;                           // 16-channel k-steps
-  uint2* bfrag = reinterpret_cast<uint2*>(osm + ((18 * 18 * pstride + 15) & ~15));  // [9][kchunks][32 lanes] B fragments
-  float2* absm = reinterpret_cast<float2*>(bfrag + 9 * kchunks * 32);              // [C]
+  uint8_t* halo = osm;                                                  // [18*18][VO_PSTRIDE]
+  uint2* bfrag = reinterpret_cast<uint2*>(osm + VO_HALO_BYTES);         // [9][VO_KC][32 lanes] B fragments of the slice
+  const int kchunks = C >> 4;                                           // k-steps of the whole contraction
   const int img = blockIdx.y;
   const int by = blockIdx.x >> 3, bx = blockIdx.x & 7;  // 8 x 8 blocks of 16 x 16 pixels per 128 x 128 image
-  for (int i = threadIdx.x; i < C; i += 512) absm[i] = ab[(long long)img * C + i];
-  // B fragment of mma.m16n8k16 (col-major k16 x n8): lane l holds W[k = 2*(l%4) + {0,1}][n = l/4] and the same at k + 8;
-  // output channels >= out_ch are zero padding
-  for (int i = threadIdx.x; i < 9 * kchunks * 32; i += 512) {
-    const int l = i & 31, kc = (i >> 5) % kchunks, tap = i / (32 * kchunks);
-    const int n = l >> 2, k0 = kc * 16 + 2 * (l & 3);
-    float v[4] = {0.f, 0.f, 0.f, 0.f};
-    if (n < out_ch) {
-      const float* wp = w + (long long)n * C * 9 + tap;
-      v[0] = wp[(k0) * 9];
-      v[1] = wp[(k0 + 1) * 9];
-      v[2] = wp[(k0 + 8) * 9];
-      v[3] = wp[(k0 + 9) * 9];
-    }
-    __half2 lo = __floats2half2_rn(v[0], v[1]), hi = __floats2half2_rn(v[2], v[3]);
-    bfrag[i] = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
-  }
-  __syncthreads();
-  const int cv = C >> 3;
+  constexpr int cv = VO_SLICE >> 3;                      // 8 chunks of 8 channels per pixel and slice
   const __half* xin = x + (long long)img * 128 * 128 * C;
-  // halo load: four 16-byte global loads in flight per thread before any dependent work.  512 is a multiple of cv, so a
-  // thread always handles the same 8-channel chunk: its GroupNorm coefficients live in registers (reading them from
-  // shared memory per item measured 16-way bank conflicts, 80 % of the kernel's smem wavefronts).
-  const int items = 18 * 18 * cv;
-  const int c8 = threadIdx.x % cv;
-  float ga[8], gb[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const float2 t = absm[c8 * 8 + j];
-    ga[j] = t.x;
-    gb[j] = t.y;
-  }
-  for (int i0 = threadIdx.x; i0 < items; i0 += 4 * 512) {
-    uint4 u[4];
-    bool inside[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const int i = i0 + k * 512;
-      const int pix = i / cv;
-      const int hy = pix / 18, hx = pix - hy * 18;
-      const int gy = by * 16 + hy - 1, gx = bx * 16 + hx - 1;
-      inside[k] = i < items && gy >= 0 && gy < 128 && gx >= 0 && gx < 128;
-      u[k] = make_uint4(0u, 0u, 0u, 0u);
-      if (inside[k]) u[k] = __ldg(reinterpret_cast<const uint4*>(xin + ((long long)gy * 128 + gx) * C) + c8);
-    }
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const int i = i0 + k * 512;
-      if (i >= items) break;
-      const int pix = i / cv;
-      uint4 o = make_uint4(0u, 0u, 0u, 0u);
-      if (inside[k]) {
-        const __half2* h2 = reinterpret_cast<const __half2*>(&u[k]);
-        __half2* o2 = reinterpret_cast<__half2*>(&o);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float2 f = __half22float2(h2[j]);
-          float v0 = fmaf(ga[2 * j], f.x, gb[2 * j]), v1 = fmaf(ga[2 * j + 1], f.y, gb[2 * j + 1]);
-          v0 = swish_fast(v0);  // the same function and rounding as gn_apply_kernel
-          v1 = swish_fast(v1);
-          o2[j] = __floats2half2_rn(v0, v1);  // the same fp16 rounding the stand-alone GroupNorm pass applies
-        }
-      }
-      *reinterpret_cast<uint4*>(halo + pix * pstride + c8 * 16) = o;
-    }
-  }
-  __syncthreads();
-  // contraction: warp w (of 16) owns output row w of the tile (one m16 tile of 16 consecutive pixels)
+  const uint32_t halo_s = static_cast<uint32_t>(__cvta_generic_to_shared(halo));
+  const uint32_t bf_s = static_cast<uint32_t>(__cvta_generic_to_shared(bfrag));
+  constexpr int items = 18 * 18 * cv;
+  const int c8 = threadIdx.x % cv;  // 512 is a multiple of cv: a thread always handles the same 8-channel chunk
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float acc[4] = {0.f, 0.f, 0.f, 0.f};
-  const uint32_t halo_s = static_cast<uint32_t>(__cvta_generic_to_shared(halo));
   // ldmatrix.x4 address of this lane: matrix m = lane / 8 covers pixels 8*(m & 1) .. +7 and channels 8*(m >> 1) .. +7
   const int lm_pix = (lane & 7) + 8 * ((lane >> 3) & 1);
   const int lm_coff = (lane >> 4) * 16;  // bytes
+  for (int c0 = 0; c0 < C; c0 += VO_SLICE) {
+    if (c0 > 0) __syncthreads();  // the previous slice's contraction has read the halo and the fragments
+    // (1) everything the slice reads from global memory is put in flight at once with cp.async (16 bytes each, no
+    // registers held): the raw halo -- out-of-image pixels are written as zeros directly: the conv pads the ACTIVATED
+    // tensor -- and the packed weight fragments of these channels
+    for (int i = threadIdx.x; i < items; i += 512) {
+      const int pix = i / cv;
+      const int hy = pix / 18, hx = pix - hy * 18;
+      const int gy = by * 16 + hy - 1, gx = bx * 16 + hx - 1;
+      const uint32_t dst = halo_s + pix * VO_PSTRIDE + c8 * 16;
+      if (gy >= 0 && gy < 128 && gx >= 0 && gx < 128) cp_async_16(dst, xin + ((long long)gy * 128 + gx) * C + c0 + c8 * 8);
+      else sts_v4(dst, make_uint4(0u, 0u, 0u, 0u));
+    }
+    for (int i = threadIdx.x; i < VO_BFRAG_BYTES / 16; i += 512) {
+      const int tap = i / (VO_KC * 16), r = i - tap * (VO_KC * 16);  // 16 pieces of 16 B per k-step
+      cp_async_16(bf_s + i * 16,
+                  reinterpret_cast<const uint4*>(bfrag_g) + ((long long)tap * kchunks + (c0 >> 4)) * 16 + r);
+    }
+    float ga[8], gb[8];
+    {
+      const float4* abp = reinterpret_cast<const float4*>(ab + (long long)img * C + c0 + c8 * 8);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float4 t = __ldg(abp + j);  // (a0, b0, a1, b1)
+        ga[2 * j] = t.x;
+        gb[2 * j] = t.y;
+        ga[2 * j + 1] = t.z;
+        gb[2 * j + 1] = t.w;
+      }
+    }
+    cp_async_wait_all();  // this thread's copies have landed (it transforms exactly the chunks it fetched)
+    // (2) GroupNorm + swish in place, shared -> shared; the same function and fp16 rounding as gn_apply_kernel
+    for (int i = threadIdx.x; i < items; i += 512) {
+      const int pix = i / cv;
+      const int hy = pix / 18, hx = pix - hy * 18;
+      const int gy = by * 16 + hy - 1, gx = bx * 16 + hx - 1;
+      if (gy >= 0 && gy < 128 && gx >= 0 && gx < 128) {
+        const uint32_t addr = halo_s + pix * VO_PSTRIDE + c8 * 16;
+        uint4 u = lds_v4(addr);
+        __half2* h2 = reinterpret_cast<__half2*>(&u);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 f = __half22float2(h2[j]);
+          const float v0 = swish_fast(fmaf(ga[2 * j], f.x, gb[2 * j]));
+          const float v1 = swish_fast(fmaf(ga[2 * j + 1], f.y, gb[2 * j + 1]));
+          h2[j] = __floats2half2_rn(v0, v1);
+        }
+        sts_v4(addr, u);
+      }
+    }
+    __syncthreads();
+    // (3) contraction: warp w (of 16) owns output row w of the tile (one m16 tile of 16 consecutive pixels)
 #pragma unroll 1
-  for (int tap = 0; tap < 9; ++tap) {
-    const int dy = tap / 3, dx = tap - dy * 3;
-    const uint2* bt = bfrag + (tap * kchunks) * 32 + lane;
-    const uint32_t a_row0 = halo_s + ((warp + dy) * 18 + dx + lm_pix) * pstride + lm_coff;
-#pragma unroll 4
-    for (int kc = 0; kc < kchunks; ++kc) {
-      const uint2 b = bt[kc * 32];
-      uint32_t a0, a1, a2, a3;
-      ldmatrix_x4(a_row0 + kc * 32, a0, a1, a2, a3);
-      mma_16816(acc, a0, a1, a2, a3, b.x, b.y);
+    for (int tap = 0; tap < 9; ++tap) {
+      const int dy = tap / 3, dx = tap - dy * 3;
+      const uint2* bt = bfrag + (tap * VO_KC) * 32 + lane;
+      const uint32_t a_row0 = halo_s + ((warp + dy) * 18 + dx + lm_pix) * VO_PSTRIDE + lm_coff;
+#pragma unroll
+      for (int kc = 0; kc < VO_KC; ++kc) {
+        const uint2 b = bt[kc * 32];
+        uint32_t a0, a1, a2, a3;
+        ldmatrix_x4(a_row0 + kc * 32, a0, a1, a2, a3);
+        mma_16816(acc, a0, a1, a2, a3, b.x, b.y);
+      }
     }
   }
   // accumulator layout: c0,c1 = (pixel lane/4, channels 2*(lane%4) + {0,1}); c2,c3 = (pixel lane/4 + 8, same channels)
@@ -774,16 +806,16 @@ __global__ void __launch_bounds__(512) vae_out_kernel(const __half* __restrict__
   }
 }
 
-cudaError_t launch_vae_out(const __half* x, const float2* ab, const float* w, const float* bias, float* roll, int n,
+cudaError_t launch_vae_out(const __half* x, const float2* ab, const void* bfrag, const float* bias, float* roll, int n,
                            int C, int out_ch, int tile0, int n_cand, int roll_len, int roll_ch, cudaStream_t s) {
-  if (C % 16 != 0 || 512 % (C / 8) != 0 || out_ch < 1 || out_ch > 8 || roll_ch > out_ch) return cudaErrorInvalidValue;
-  const size_t smem = ((18 * 18 * (C * 2 + 16) + 15) & ~15) + (size_t)9 * (C / 16) * 32 * sizeof(uint2) +
-                      (size_t)C * sizeof(float2);
+  if (C % VO_SLICE != 0 || out_ch < 1 || out_ch > 8 || roll_ch > out_ch) return cudaErrorInvalidValue;
+  const size_t smem = VO_HALO_BYTES + VO_BFRAG_BYTES;
   static SmemAttr attr;
   if (cudaError_t e = attr.ensure(vae_out_kernel, smem); e != cudaSuccess) return e;
   ProfScope prof("vae_out(norm+swish+conv_out+roll)", 2.0 * n * 16384.0 * out_ch * 9.0 * C, 2.0 * n * 16384.0 * 8 * 9.0 * C,
                  (double)n * 16384.0 * (C * 2.0 + roll_ch * 4.0), s);
-  vae_out_kernel<<<dim3(64, n), 512, smem, s>>>(x, ab, w, bias, roll, C, out_ch, tile0, n_cand, roll_len, roll_ch);
+  vae_out_kernel<<<dim3(64, n), 512, smem, s>>>(x, ab, static_cast<const uint2*>(bfrag), bias, roll, C, out_ch, tile0,
+                                                n_cand, roll_len, roll_ch);
   return done();
 }
 

@@ -481,8 +481,9 @@ int rgm_dit_forward(rgm_dit* h, const float* x, const float* t, const long long*
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (B <= 0) return 0;
   const int T = H * m->tpt;
-  if (T != 128 && T != 256)
-    return set_error("rgm_dit_forward: " + std::to_string(T) + " tokens; this build supports 128 or 256 (latent H 64 or 128 at patch 8)");
+  if (T < 64 || T > 256 || T % 64 != 0)
+    return set_error("rgm_dit_forward: " + std::to_string(T) + " tokens; this build supports 64, 128, 192 or 256 (latent H "
+                     "32 ... 128 in steps of 32 at patch 8; the reference's checkpoints are trained at H = 128)");
   if (dit_prepare(m, B, T, st) != 0) return -1;
   const int chunk = m->chunk < B ? m->chunk : B;
   const int n_chunks = (B + chunk - 1) / chunk;

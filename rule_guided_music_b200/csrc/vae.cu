@@ -59,7 +59,8 @@ struct Vae {
   std::vector<std::vector<Res>> up;     // [level][block]
   std::vector<Conv> upsample;           // [level] (level 0 unused)
   Norm norm_out;
-  float *cout_w = nullptr, *cout_b = nullptr;  // conv_out stays fp32: it runs fused on the CUDA cores (vae_out_kernel)
+  float *cout_w = nullptr, *cout_b = nullptr;  // conv_out stays fp32 at load; it runs fused on mma.sync (vae_out_kernel)
+  void* cout_bfrag = nullptr;                  // ... from fp16 B fragments packed once per weight load
   int cout_cin = 0;
   // encoder (model.py:342-433) + quant_conv
   int in_ch = 3;
@@ -175,7 +176,8 @@ int vae_build(Vae* m) {
   m->cout_cin = block_in;
   m->cout_w = m->alloc<float>((long long)m->out_ch * block_in * 9);
   m->cout_b = m->alloc<float>(m->out_ch);
-  if (!ok || !m->cout_w || !m->cout_b) return set_error("rgm_vae_create: out of memory");
+  m->cout_bfrag = m->alloc<uint2>(9LL * (block_in / 16) * 32);
+  if (!ok || !m->cout_w || !m->cout_b || !m->cout_bfrag) return set_error("rgm_vae_create: out of memory");
   m->f32_keys["decoder.conv_out.weight"] = {m->cout_w, (long long)m->out_ch * block_in * 9};
   m->f32_keys["decoder.conv_out.bias"] = {m->cout_b, m->out_ch};
 
@@ -435,7 +437,7 @@ int decode_chunk(Vae* m, Vae::Lane* L, const float* lat, float scale, float* rol
   // norm_out + swish + conv_out, assembled into the roll: one fused CUDA-core kernel (aux_kernels.cu)
   {
     if (H != 128) return set_error("rgm_vae: decoder output is not 128x128 (the roll kernels assume 128x128 tiles)");
-    RGM_CUDA_OK(launch_vae_out(buf[cur], c.ab(), m->cout_w, m->cout_b, roll, nt, m->norm_out.c, m->out_ch, tile0, n_cand,
+    RGM_CUDA_OK(launch_vae_out(buf[cur], c.ab(), m->cout_bfrag, m->cout_b, roll, nt, m->norm_out.c, m->out_ch, tile0, n_cand,
                                8 * Hlat, roll_ch, st));
   }
   return 0;
@@ -622,8 +624,10 @@ int rgm_vae_load(rgm_vae* h, const char* key, const float* src, long long numel,
   if (f != m->f32_keys.end()) {
     if (numel != f->second.second)
       return set_error("rgm_vae_load: " + k + ": expected " + std::to_string(f->second.second) + " elements");
-    return check_cuda(cudaMemcpyAsync(f->second.first, src, (size_t)numel * sizeof(float), cudaMemcpyDeviceToDevice, st),
-                      "rgm_vae_load");
+    RGM_CUDA_OK(cudaMemcpyAsync(f->second.first, src, (size_t)numel * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    if (k == "decoder.conv_out.weight")
+      RGM_CUDA_OK(launch_vae_out_pack(m->cout_w, m->cout_bfrag, m->cout_cin, m->out_ch, st));
+    return 0;
   }
   auto cv = m->conv_keys.find(k);
   if (cv == m->conv_keys.end()) return 1;  // encoder / loss / quant_conv tensors: not on this path

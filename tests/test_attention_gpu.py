@@ -10,7 +10,8 @@ pytestmark = pytest.mark.gpu
 
 
 @pytest.mark.parametrize("B,heads,T,dh", [(1, 1, 128, 64), (2, 3, 256, 72), (3, 16, 256, 72), (40, 16, 128, 72),
-                                           (2, 2, 256, 128), (5, 6, 128, 64)])
+                                           (2, 2, 256, 128), (5, 6, 128, 64), (3, 4, 192, 72), (7, 2, 64, 64),
+                                           (1, 16, 192, 72)])
 def test_attention(cuda, B, heads, T, dh):
     g = torch.Generator(device="cpu").manual_seed(B * 100 + heads + T + dh)
     q = torch.randn(B, heads, T, dh, generator=g).to(cuda).half()

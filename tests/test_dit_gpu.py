@@ -55,6 +55,23 @@ def test_dit_batch_chunking_and_no_label(cuda, monkeypatch, parity):
     assert parity("DiT forward small, y=None, vs oracle", gpu_util.rel_l2(out, ref), TOL) < TOL
 
 
+@pytest.mark.parametrize("H", [32, 96])
+def test_dit_other_latent_lengths(cuda, H, parity):
+    """The reference's DiTRotary accepts any latent length (dit.py:618-634); the native one takes 64 / 128 / 192 / 256
+    tokens.  T = 64 and T = 192 (half-full last query tile in the attention kernel) against the oracle."""
+    cfg = gi.DIT_CASES["small"]
+    model, sd = gpu_util.native_dit(cfg, cuda)
+    g = torch.Generator(device="cpu").manual_seed(H)
+    x = torch.randn(3, 4, H, 16, generator=g)
+    t = torch.tensor([900, 40, 512])
+    y = torch.tensor([0, 2, 1])
+    w = cfg["weights"]
+    with torch.no_grad():
+        ref = odit.dit_forward(sd, x, t, y, heads=w["heads"], patch=w["patch"])
+    out = model(x.to(cuda), t.to(cuda), y.to(cuda)).cpu()
+    assert parity(f"DiT forward small T={2 * H} vs oracle", gpu_util.rel_l2(out, ref), TOL) < TOL
+
+
 def test_dit_rejects_cpu_and_bad_shapes(cuda):
     from rule_guided_music_b200 import _lib
     from rule_guided_music_b200.guided_diffusion.dit import DiT_models
@@ -64,4 +81,4 @@ def test_dit_rejects_cpu_and_bad_shapes(cuda):
         m.to("cpu")
     m.to(cuda)
     with pytest.raises(_lib.RgmError):
-        m(torch.zeros(1, 4, 32, 16, device=cuda), torch.zeros(1, device=cuda), None)  # 64 tokens: unsupported
+        m(torch.zeros(1, 4, 40, 16, device=cuda), torch.zeros(1, device=cuda), None)  # 80 tokens: unsupported

@@ -24,11 +24,28 @@ y = torch.ones(B, dtype=torch.long, device=dev)
 lat = torch.randn(16, 4, 128, 16, device=dev)
 
 
+from rule_guided_music_b200 import _lib  # noqa: E402
+from rule_guided_music_b200.music_rule_guidance import music_rules  # noqa: E402
+
+# the fused GroupNorm + conv kernel at one bench chunk's shape (opt-in path, profiled for the bound analysis)
+n_cg, cin = 128, 128
+xg = torch.randn(n_cg, 128, 128, cin, device=dev).half()
+abg = torch.stack((torch.rand(n_cg, cin, device=dev) + 0.5, torch.randn(n_cg, cin, device=dev) * 0.3), dim=-1).contiguous()
+wg = torch.randn(128 * 9 * cin, device=dev).half() * 0.02
+bg = torch.zeros(128, device=dev)
+og = torch.empty(n_cg, 128, 128, 128, device=dev, dtype=torch.float16)
+
+
 def run():
     if part in ("dit", "all"):
         model(x, t, y)
     if part in ("vae", "all"):
-        vae.decode_latents(lat, 1.2465, channels=1)
+        roll = vae.decode_latents(lat, 1.2465, channels=1)
+        music_rules.total_pitch_class_histogram(roll)
+        music_rules.note_density(roll)
+    if part in ("convgn",):
+        _lib.call("rgm_conv_gn_f16", _lib.ptr(xg), _lib.ptr(abg), _lib.ptr(wg), _lib.ptr(bg), None, _lib.ptr(og), n_cg, 128,
+                  128, cin, 128, None, _lib.stream_ptr())
 
 
 run()

@@ -118,3 +118,34 @@ def test_scg_refuses_learned_variance_like_the_reference():
     with pytest.raises(AssertionError):
         d.scg_sample(lambda *a, **k: x, torch.zeros(1, dtype=torch.long), x, x, None, 1.0,
                      model_kwargs={"y": torch.zeros(1, dtype=torch.long), "rule": {}}, scg_kwargs={"num_samples": 2})
+
+
+def _build_c_host(tmp_path):
+    import os
+    import shutil
+    import subprocess
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    exe = str(tmp_path / "scg_step_host")
+    cuda_lib = "/usr/local/cuda/lib64"
+    cmd = ["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(root, "include"),
+           os.path.join(root, "examples", "scg_step_host.c"), "-L", os.path.dirname(_lib.LIB_PATH), "-lrgm_b200", "-L", cuda_lib,
+           "-lcudart", "-lm", "-o", exe]
+    out = subprocess.run(cmd, capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    env = dict(os.environ, LD_LIBRARY_PATH=os.path.dirname(_lib.LIB_PATH) + ":" + cuda_lib + ":" + os.environ.get("LD_LIBRARY_PATH", ""))
+    return exe, env
+
+
+def test_header_is_valid_c_and_a_c_host_links(tmp_path):
+    """include/rgm_b200.h compiles as C99 and examples/scg_step_host.c -- a whole DDIM + SCG step with no Python -- links
+    against the library.  Without a B200 the program must refuse to compute (exit code 2), not fall back."""
+    import subprocess
+
+    exe, env = _build_c_host(tmp_path)
+    if torch.cuda.is_available():
+        return
+    out = subprocess.run([exe], capture_output=True, text=True, env=env, timeout=120)
+    assert out.returncode == 2 and "no CPU path" in out.stderr

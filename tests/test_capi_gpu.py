@@ -207,3 +207,15 @@ def test_rule_target_shape_is_checked(cuda):
     with pytest.raises(_lib.RgmError):
         d.scg_sample(d._wrap_model(fn), torch.full((B,), 3, device=cuda), mean, torch.ones_like(mean) * 0.1, vae, 1.0,
                      model_kwargs=mk, scg_kwargs={"num_samples": 2})
+
+
+def test_c_host_runs_a_whole_step(cuda, tmp_path):
+    """examples/scg_step_host.c: a C99 program (no Python, no torch) runs DiT -> rgm_ddim_mean -> rgm_scg_step on a B200."""
+    import subprocess
+
+    from test_capi_cpu import _build_c_host
+
+    exe, env = _build_c_host(tmp_path)
+    out = subprocess.run([exe], capture_output=True, text=True, env=env, timeout=300)
+    assert out.returncode == 0, out.stderr + out.stdout
+    assert "scg step ok" in out.stdout

@@ -658,18 +658,25 @@ __device__ __forceinline__ void mma_16816(float (&c)[4], uint32_t a0, uint32_t a
       : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
 
-// B fragments of mma.m16n8k16 for the conv_out weights (col-major k16 x n8): entry [tap][kc][lane] holds
-// W[k = kc*16 + 2*(lane%4) + {0,1}][n = lane/4] and the same at k + 8 as two half2; output channels >= out_ch are zero
-// padding.  Packed ONCE when the weights are loaded (it used to be rebuilt by each of the 8192 blocks of a launch).
-__global__ void vae_out_pack_kernel(const float* __restrict__ w, uint2* __restrict__ bfrag, int C, int out_ch) {
+// conv_out weights as B fragments of mma.m16n8k16 (col-major k16 x n8) for the "one A fragment serves the three dx taps"
+// contraction of vae_out_kernel: for a kernel ROW dy the B matrix is [K = input channels][N = (dx, out channel)], so
+// Y_dy[q][(dx, co)] = sum_k act[q][k] * W[co][k][dy][dx] for every halo pixel q, and
+// out[r][c][co] = sum_dy sum_dx Y_dy[(r + dy) * 18 + c + dx][(dx, co)].
+// Two packings, built ONCE when the weights are loaded: NF = 1 -- columns n = dx (output channel 0 only: what the SCG
+// rules read) -- and NF = 2 -- columns n = dx * out_ch + co (all channels, <= 16 columns).  Entry
+// [dy][kc][nf][lane] = (W[k0][n], W[k0+1][n]) and (W[k0+8][n], W[k0+9][n]) as two half2, k0 = kc*16 + 2*(lane%4),
+// n = nf*8 + lane/4; columns past the last real one are zero.
+__global__ void vae_out_pack_kernel(const float* __restrict__ w, uint2* __restrict__ bfrag, int C, int out_ch, int NF) {
   const int kchunks = C >> 4;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= 9 * kchunks * 32) return;
-  const int l = i & 31, kc = (i >> 5) % kchunks, tap = i / (32 * kchunks);
-  const int n = l >> 2, k0 = kc * 16 + 2 * (l & 3);
+  if (i >= 3 * kchunks * NF * 32) return;
+  const int l = i & 31, nf = (i >> 5) % NF, kc = (i / (32 * NF)) % kchunks, dy = i / (32 * NF * kchunks);
+  const int n = nf * 8 + (l >> 2), k0 = kc * 16 + 2 * (l & 3);
+  const int cols_per_dx = NF == 1 ? 1 : out_ch;
+  const int dx = n / cols_per_dx, co = n - dx * cols_per_dx;
   float v[4] = {0.f, 0.f, 0.f, 0.f};
-  if (n < out_ch) {
-    const float* wp = w + (long long)n * C * 9 + tap;
+  if (dx < 3 && co < out_ch) {
+    const float* wp = w + (long long)co * C * 9 + dy * 3 + dx;  // torch layout [out_ch][C][3][3]
     v[0] = wp[(k0) * 9];
     v[1] = wp[(k0 + 1) * 9];
     v[2] = wp[(k0 + 8) * 9];
@@ -679,10 +686,12 @@ __global__ void vae_out_pack_kernel(const float* __restrict__ w, uint2* __restri
   bfrag[i] = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
 }
 
+// bfrag: room for both packings back to back: 3 * C/16 * 32 uint2 (NF = 1) then 3 * C/16 * 2 * 32 uint2 (NF = 2)
 cudaError_t launch_vae_out_pack(const float* w, void* bfrag, int C, int out_ch, cudaStream_t s) {
-  if (C % 16 != 0 || out_ch < 1 || out_ch > 8) return cudaErrorInvalidValue;
-  const int n = 9 * (C / 16) * 32;
-  vae_out_pack_kernel<<<(n + 255) / 256, 256, 0, s>>>(w, static_cast<uint2*>(bfrag), C, out_ch);
+  if (C % 16 != 0 || out_ch < 1 || 3 * out_ch > 16) return cudaErrorInvalidValue;
+  const int n1 = 3 * (C / 16) * 32;
+  vae_out_pack_kernel<<<(n1 + 255) / 256, 256, 0, s>>>(w, static_cast<uint2*>(bfrag), C, out_ch, 1);
+  vae_out_pack_kernel<<<(2 * n1 + 255) / 256, 256, 0, s>>>(w, static_cast<uint2*>(bfrag) + n1, C, out_ch, 2);
   return done();
 }
 
@@ -693,53 +702,82 @@ __device__ __forceinline__ void cp_async_wait_all() {
   asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
 }
 
-// The input channels are processed in SLICES of 64 (one 18x18x64 halo = 46 KB + 9 KB of weight fragments per block):
-// four blocks fit an SM, so one block's loads and tensor-core contraction overlap the others' MUFU-bound activation
-// (with the whole 128-channel halo resident only two blocks fit and the phases of a block ran back to back).
+// norm_out (GroupNorm apply + swish, model.py:533-535) + conv_out 3x3 C -> out_ch (model.py:536) + assembly of the piano
+// roll (gaussian_diffusion.py:1355) in one kernel.  One block = 16x16 output pixels of one tile.  Per SLICE of 64 input
+// channels: the raw 18x18 halo arrives by cp.async (everything in flight at once), is normalised + activated in place
+// (out-of-image pixels stay zero: the conv pads the ACTIVATED tensor; gn_apply_kernel's arithmetic and rounding), and is
+// contracted on mma.sync m16n8k16 with the halo FLATTENED to 324 (+12 padding) pixels = 21 m16 tiles: one ldmatrix
+// fragment of 16 consecutive halo pixels serves all three dx taps of a kernel row (they are columns of the B matrix) and
+// all three rows dy (three B fragments) -- 4x fewer shared-memory wavefronts than nine shifted fragment loads per
+// output row, which is what bounded the previous form (ncu: 84 M shared wavefronts per launch, 72 % of its cycles).
+// The per-(dy, halo pixel, dx) partial products then go through shared memory once and each output pixel sums its nine.
 constexpr int VO_SLICE = 64;
 constexpr int VO_PSTRIDE = VO_SLICE * 2 + 16;           // bytes per halo pixel: 16 B of padding -> conflict-free ldmatrix
-constexpr int VO_HALO_BYTES = 18 * 18 * VO_PSTRIDE;     // 46 656
+constexpr int VO_HALO_PIX = 18 * 18;                    // 324
+constexpr int VO_TILES = (VO_HALO_PIX + 15) / 16;       // 21 m16 tiles over the flattened halo
+constexpr int VO_HALO_BYTES = VO_TILES * 16 * VO_PSTRIDE;  // 48 384 (pixels 324..335 are zero padding)
 constexpr int VO_KC = VO_SLICE / 16;                    // k-steps per slice
-constexpr int VO_BFRAG_BYTES = 9 * VO_KC * 32 * 8;      // 9 216
+constexpr int VO_WARPS = 16;
 
-__global__ void __launch_bounds__(512, 4) vae_out_kernel(const __half* __restrict__ x, const float2* __restrict__ ab,
-                                                         const uint2* __restrict__ bfrag_g, const float* __restrict__ bias,
-                                                         float* __restrict__ roll, int C, int out_ch, int tile0,
-                                                         int n_cand, int roll_len, int roll_ch) {
+template <int NF>
+__global__ void __launch_bounds__(32 * VO_WARPS, NF == 1 ? 2 : 1) vae_out_kernel(const __half* __restrict__ x, const float2* __restrict__ ab,
+                                                                  const uint2* __restrict__ bfrag_g,
+                                                                  const float* __restrict__ bias, float* __restrict__ roll,
+                                                                  int C, int tile0, int n_cand, int roll_len,
+                                                                  int roll_ch) {
   extern __shared__ __align__(16) uint8_t osm[];
-  uint8_t* halo = osm;                                                  // [18*18][VO_PSTRIDE]
-  uint2* bfrag = reinterpret_cast<uint2*>(osm + VO_HALO_BYTES);         // [9][VO_KC][32 lanes] B fragments of the slice
-  const int kchunks = C >> 4;                                           // k-steps of the whole contraction
+  // two slice buffers: [336][VO_PSTRIDE] halo + [3][VO_KC][NF][32 lanes] weight fragments each (buffer 0 later holds Y)
+  constexpr int BF_BYTES = 3 * VO_KC * NF * 32 * 8;
+  constexpr int BUF_BYTES = VO_HALO_BYTES + BF_BYTES;
+  const int kchunks = C >> 4;
   const int img = blockIdx.y;
   const int by = blockIdx.x >> 3, bx = blockIdx.x & 7;  // 8 x 8 blocks of 16 x 16 pixels per 128 x 128 image
   constexpr int cv = VO_SLICE >> 3;                      // 8 chunks of 8 channels per pixel and slice
+  constexpr int NT = 32 * VO_WARPS;
   const __half* xin = x + (long long)img * 128 * 128 * C;
-  const uint32_t halo_s = static_cast<uint32_t>(__cvta_generic_to_shared(halo));
-  const uint32_t bf_s = static_cast<uint32_t>(__cvta_generic_to_shared(bfrag));
-  constexpr int items = 18 * 18 * cv;
-  const int c8 = threadIdx.x % cv;  // 512 is a multiple of cv: a thread always handles the same 8-channel chunk
+  const uint32_t osm_s = static_cast<uint32_t>(__cvta_generic_to_shared(osm));
+  constexpr int items = VO_TILES * 16 * cv;  // padding pixels included (written as zeros)
+  const int c8 = threadIdx.x % cv;           // NT is a multiple of cv: a thread always handles the same 8-channel chunk
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  float acc[2][3][NF][4];
+#pragma unroll
+  for (int i = 0; i < 2 * 3 * NF * 4; ++i) (&acc[0][0][0][0])[i] = 0.f;
   // ldmatrix.x4 address of this lane: matrix m = lane / 8 covers pixels 8*(m & 1) .. +7 and channels 8*(m >> 1) .. +7
   const int lm_pix = (lane & 7) + 8 * ((lane >> 3) & 1);
   const int lm_coff = (lane >> 4) * 16;  // bytes
-  for (int c0 = 0; c0 < C; c0 += VO_SLICE) {
-    if (c0 > 0) __syncthreads();  // the previous slice's contraction has read the halo and the fragments
-    // (1) everything the slice reads from global memory is put in flight at once with cp.async (16 bytes each, no
-    // registers held): the raw halo -- out-of-image pixels are written as zeros directly: the conv pads the ACTIVATED
-    // tensor -- and the packed weight fragments of these channels
-    for (int i = threadIdx.x; i < items; i += 512) {
+  constexpr int bf_pieces = BF_BYTES / 16;  // 16-byte pieces of one slice's fragments
+  // everything a slice reads from global memory goes in flight at once with cp.async (16 bytes each, no registers held),
+  // one commit group per slice; slice s + 1 is fetched into the other buffer while slice s is normalised and contracted
+  auto fetch = [&](int c0, int buf) {
+    const uint32_t halo_s = osm_s + buf * BUF_BYTES;
+    for (int i = threadIdx.x; i < items; i += NT) {
       const int pix = i / cv;
       const int hy = pix / 18, hx = pix - hy * 18;
       const int gy = by * 16 + hy - 1, gx = bx * 16 + hx - 1;
       const uint32_t dst = halo_s + pix * VO_PSTRIDE + c8 * 16;
-      if (gy >= 0 && gy < 128 && gx >= 0 && gx < 128) cp_async_16(dst, xin + ((long long)gy * 128 + gx) * C + c0 + c8 * 8);
-      else sts_v4(dst, make_uint4(0u, 0u, 0u, 0u));
+      if (pix < VO_HALO_PIX && gy >= 0 && gy < 128 && gx >= 0 && gx < 128)
+        cp_async_16(dst, xin + ((long long)gy * 128 + gx) * C + c0 + c8 * 8);
+      else
+        sts_v4(dst, make_uint4(0u, 0u, 0u, 0u));
     }
-    for (int i = threadIdx.x; i < VO_BFRAG_BYTES / 16; i += 512) {
-      const int tap = i / (VO_KC * 16), r = i - tap * (VO_KC * 16);  // 16 pieces of 16 B per k-step
-      cp_async_16(bf_s + i * 16,
-                  reinterpret_cast<const uint4*>(bfrag_g) + ((long long)tap * kchunks + (c0 >> 4)) * 16 + r);
+    for (int i = threadIdx.x; i < bf_pieces; i += NT) {
+      constexpr int per_dy = VO_KC * NF * 16;  // pieces per kernel row of the slice
+      const int dy = i / per_dy, r = i - dy * per_dy;
+      cp_async_16(halo_s + VO_HALO_BYTES + i * 16,
+                  reinterpret_cast<const uint4*>(bfrag_g) + ((long long)dy * kchunks + (c0 >> 4)) * NF * 16 + r);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  fetch(0, 0);
+  int sl = 0;
+  for (int c0 = 0; c0 < C; c0 += VO_SLICE, ++sl) {
+    const int buf = sl & 1;
+    const uint32_t halo_s = osm_s + buf * BUF_BYTES;
+    const uint2* bfrag = reinterpret_cast<const uint2*>(osm + buf * BUF_BYTES + VO_HALO_BYTES);
+    const bool more = c0 + VO_SLICE < C;
+    if (more) {
+      if (sl >= 1) __syncthreads();  // the contraction of slice s - 1 has read the buffer slice s + 1 goes into
+      fetch(c0 + VO_SLICE, buf ^ 1);
     }
     float ga[8], gb[8];
     {
@@ -753,9 +791,10 @@ __global__ void __launch_bounds__(512, 4) vae_out_kernel(const __half* __restric
         gb[2 * j + 1] = t.w;
       }
     }
-    cp_async_wait_all();  // this thread's copies have landed (it transforms exactly the chunks it fetched)
-    // (2) GroupNorm + swish in place, shared -> shared; the same function and fp16 rounding as gn_apply_kernel
-    for (int i = threadIdx.x; i < items; i += 512) {
+    // this thread's copies of slice s have landed (it transforms exactly the chunks it fetched)
+    if (more) asm volatile("cp.async.wait_group 1;" ::: "memory");
+    else asm volatile("cp.async.wait_group 0;" ::: "memory");
+    for (int i = threadIdx.x; i < VO_HALO_PIX * cv; i += NT) {
       const int pix = i / cv;
       const int hy = pix / 18, hx = pix - hy * 18;
       const int gy = by * 16 + hy - 1, gx = bx * 16 + hx - 1;
@@ -774,48 +813,81 @@ __global__ void __launch_bounds__(512, 4) vae_out_kernel(const __half* __restric
       }
     }
     __syncthreads();
-    // (3) contraction: warp w (of 16) owns output row w of the tile (one m16 tile of 16 consecutive pixels)
-#pragma unroll 1
-    for (int tap = 0; tap < 9; ++tap) {
-      const int dy = tap / 3, dx = tap - dy * 3;
-      const uint2* bt = bfrag + (tap * VO_KC) * 32 + lane;
-      const uint32_t a_row0 = halo_s + ((warp + dy) * 18 + dx + lm_pix) * VO_PSTRIDE + lm_coff;
+    // contraction: warp w owns halo-pixel tiles w and w + 16 (21 tiles)
 #pragma unroll
-      for (int kc = 0; kc < VO_KC; ++kc) {
-        const uint2 b = bt[kc * 32];
-        uint32_t a0, a1, a2, a3;
-        ldmatrix_x4(a_row0 + kc * 32, a0, a1, a2, a3);
-        mma_16816(acc, a0, a1, a2, a3, b.x, b.y);
+    for (int ti = 0; ti < 2; ++ti) {
+      const int tile = warp + ti * VO_WARPS;
+      if (tile < VO_TILES) {
+        const uint32_t a_row0 = halo_s + (tile * 16 + lm_pix) * VO_PSTRIDE + lm_coff;
+#pragma unroll
+        for (int kc = 0; kc < VO_KC; ++kc) {
+          uint32_t a0, a1, a2, a3;
+          ldmatrix_x4(a_row0 + kc * 32, a0, a1, a2, a3);
+#pragma unroll
+          for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+            for (int nf = 0; nf < NF; ++nf) {
+              const uint2 b = bfrag[((dy * VO_KC + kc) * NF + nf) * 32 + lane];
+              mma_16816(acc[ti][dy][nf], a0, a1, a2, a3, b.x, b.y);
+            }
+        }
       }
     }
   }
-  // accumulator layout: c0,c1 = (pixel lane/4, channels 2*(lane%4) + {0,1}); c2,c3 = (pixel lane/4 + 8, same channels)
+  __syncthreads();  // every warp is done with the halo: its memory now holds Y[dy][halo pixel][8 * NF columns] fp32
+  float* Y = reinterpret_cast<float*>(osm);  // 3 * 336 * 8 * NF floats <= two slice buffers
+  constexpr int YC = 8 * NF;
+  // accumulator layout: c0,c1 = (pixel lane/4, columns 2*(lane%4) + {0,1}); c2,c3 = (pixel lane/4 + 8, same columns)
+#pragma unroll
+  for (int ti = 0; ti < 2; ++ti) {
+    const int tile = warp + ti * VO_WARPS;
+    if (tile < VO_TILES) {
+#pragma unroll
+      for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+        for (int nf = 0; nf < NF; ++nf) {
+          float* yp = Y + ((dy * (VO_TILES * 16) + tile * 16 + (lane >> 2)) * YC) + nf * 8 + 2 * (lane & 3);
+          *reinterpret_cast<float2*>(yp) = make_float2(acc[ti][dy][nf][0], acc[ti][dy][nf][1]);
+          *reinterpret_cast<float2*>(yp + 8 * YC) = make_float2(acc[ti][dy][nf][2], acc[ti][dy][nf][3]);
+        }
+    }
+  }
+  __syncthreads();
+  // each output pixel sums its nine partial products; consecutive threads = consecutive time columns of a roll row
   const int g = tile0 + img;  // global tile index, tile-major: g = k * n_cand + cand
   const int kt = g / n_cand, cand = g - kt * n_cand;
-  const int ch0 = 2 * (lane & 3);
-  const int h = by * 16 + warp;
-  const int wcol = kt * 128 + bx * 16 + (lane >> 2);
+  const int cols_per_dx = NF == 1 ? 1 : 3;
+  for (int o = threadIdx.x; o < 256 * roll_ch; o += NT) {
+    const int ch = o >> 8, r = (o >> 4) & 15, c = o & 15;
+    float v = bias[ch];
 #pragma unroll
-  for (int j = 0; j < 2; ++j) {
-    const int ch = ch0 + j;
-    if (ch < roll_ch) {
-      float* dst = roll + (((long long)cand * roll_ch + ch) * 128 + h) * roll_len + wcol;
-      dst[0] = acc[j] + bias[ch];
-      dst[8] = acc[2 + j] + bias[ch];
-    }
+    for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+      for (int dx = 0; dx < 3; ++dx)
+        v += Y[(dy * (VO_TILES * 16) + (r + dy) * 18 + c + dx) * YC + dx * cols_per_dx + ch];
+    roll[(((long long)cand * roll_ch + ch) * 128 + by * 16 + r) * roll_len + kt * 128 + bx * 16 + c] = v;
   }
 }
 
 cudaError_t launch_vae_out(const __half* x, const float2* ab, const void* bfrag, const float* bias, float* roll, int n,
                            int C, int out_ch, int tile0, int n_cand, int roll_len, int roll_ch, cudaStream_t s) {
-  if (C % VO_SLICE != 0 || out_ch < 1 || out_ch > 8 || roll_ch > out_ch) return cudaErrorInvalidValue;
-  const size_t smem = VO_HALO_BYTES + VO_BFRAG_BYTES;
-  static SmemAttr attr;
-  if (cudaError_t e = attr.ensure(vae_out_kernel, smem); e != cudaSuccess) return e;
+  if (C % VO_SLICE != 0 || out_ch != 3 || roll_ch < 1 || roll_ch > out_ch) return cudaErrorInvalidValue;
   ProfScope prof("vae_out(norm+swish+conv_out+roll)", 2.0 * n * 16384.0 * out_ch * 9.0 * C, 2.0 * n * 16384.0 * 8 * 9.0 * C,
                  (double)n * 16384.0 * (C * 2.0 + roll_ch * 4.0), s);
-  vae_out_kernel<<<dim3(64, n), 512, smem, s>>>(x, ab, static_cast<const uint2*>(bfrag), bias, roll, C, out_ch, tile0,
-                                                n_cand, roll_len, roll_ch);
+  const uint2* bf = static_cast<const uint2*>(bfrag);
+  const int n1 = 3 * (C / 16) * 32;  // uint2 entries of the one-channel packing (launch_vae_out_pack)
+  if (roll_ch == 1) {  // the SCG path: the rules read channel 0 only
+    const size_t smem = 2 * (VO_HALO_BYTES + 3 * VO_KC * 1 * 32 * 8);  // two slice buffers; the partial products reuse them
+    static SmemAttr attr;
+    if (cudaError_t e = attr.ensure(vae_out_kernel<1>, smem); e != cudaSuccess) return e;
+    vae_out_kernel<1><<<dim3(64, n), 32 * VO_WARPS, smem, s>>>(x, ab, bf, bias, roll, C, tile0, n_cand, roll_len, roll_ch);
+  } else {
+    const size_t smem = 2 * (VO_HALO_BYTES + 3 * VO_KC * 2 * 32 * 8);  // 63 KB of partial products fit the two buffers
+    static SmemAttr attr;
+    if (cudaError_t e = attr.ensure(vae_out_kernel<2>, smem); e != cudaSuccess) return e;
+    vae_out_kernel<2><<<dim3(64, n), 32 * VO_WARPS, smem, s>>>(x, ab, bf + n1, bias, roll, C, tile0, n_cand, roll_len,
+                                                              roll_ch);
+  }
   return done();
 }
 

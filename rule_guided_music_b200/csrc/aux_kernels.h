@@ -48,7 +48,8 @@ cudaError_t launch_gn_apply(const __half* x, const float2* ab, __half* y, int n,
                             cudaStream_t s);
 // norm_out + swish + conv_out (3x3, C -> out_ch <= 4, fp32 weights [out_ch,C,3,3]) + roll assembly, CUDA cores:
 // x fp16 NHWC [n,128,128,C] (raw, before GroupNorm), ab its GroupNorm affine, roll f32 [n_cand, roll_ch, 128, roll_len]
-// bfrag = the conv_out weights packed by launch_vae_out_pack (mma.m16n8k16 B fragments, 9 * C/16 * 32 uint2)
+// bfrag = the conv_out weights packed by launch_vae_out_pack (mma.m16n8k16 B fragments, 9 * C/16 * 32 uint2 in all:
+// the channel-0 packing followed by the three-channel packing); out_ch must be 3
 cudaError_t launch_vae_out(const __half* x, const float2* ab, const void* bfrag, const float* bias, float* roll, int n,
                            int C, int out_ch, int tile0, int n_cand, int roll_len, int roll_ch, cudaStream_t s);
 cudaError_t launch_vae_out_pack(const float* w, void* bfrag, int C, int out_ch, cudaStream_t s);

@@ -564,7 +564,7 @@ int rgm_vae_create(rgm_vae** out, int ch, const int* ch_mult, int n_levels, int 
   if (rgm_check_device()) return -1;
   if (!out || !ch_mult || n_levels < 1 || n_levels > 8) return set_error("rgm_vae_create: bad arguments");
   if (z_channels != 4) return set_error("rgm_vae_create: the fused stem is written for z_channels = 4");
-  if (out_ch > 8) return set_error("rgm_vae_create: out_ch > 8 (the fused conv_out kernel pads the output channels to 8)");
+  if (out_ch != 3) return set_error("rgm_vae_create: out_ch must be 3 (piano roll, onset, pedal: the fused conv_out kernel is written for it)");
   Vae* m = new Vae();
   m->ch = ch;
   m->n_levels = n_levels;

@@ -72,6 +72,10 @@ typedef struct rgm_vae rgm_vae;
 int rgm_vae_create(rgm_vae** out, int ch, const int* ch_mult_host, int n_levels, int num_res_blocks, int z_channels,
                    int out_ch);
 int rgm_vae_destroy(rgm_vae* h);
+/* Diagnostic: 1 if a convolution that normalises its own output (GroupNorm statistics exchanged between CTAs while the
+ * accumulators wait in tensor memory) ever gave up waiting for its image's other tiles -- never in a healthy run; 0
+ * otherwise; negative on error.  Synchronises the device. */
+int rgm_vae_gn_timeouts(rgm_vae* h);
 /* Pre-size the activation buffers for decodes / encodes of up to n_tiles 16x16 latent tiles (same contract as
  * rgm_dit_reserve). */
 int rgm_vae_reserve(rgm_vae* h, int n_tiles);
@@ -197,6 +201,15 @@ int rgm_gn_apply_f16(const void* x16, const float* ab, void* y16, int n_img, int
 int rgm_conv_gn_f16(const void* x16_raw, const float* ab_in, const void* w16_packed, const float* bias,
                     const void* resid16, void* out16, int n_img, int H, int W, int Cin, int Cout, float* gn_part,
                     void* stream);
+/* swish(GroupNorm_32(conv(x))) in ONE kernel with the normalisation applied to the convolution's OWN output
+ * (reference model.py:119-124: h = conv1(..); h = norm2(h); h = nonlinearity(h)): the CTAs of an image exchange their
+ * partial statistics while the accumulators wait in tensor memory, so the raw output is never written.  kind 0 / 1,
+ * Cout in {128, 256, 512}, H*W a multiple of 256; gamma / beta f32 [Cout]; gn_scratch: n * 512 bytes of device
+ * scratch (per-group statistics accumulators that also count arrivals, zeroed by the call); gn_err: device int that is set to 1
+ * if a wait gives up (never in a healthy run).  swish = 0 applies the norm only. */
+int rgm_conv_norm_f16(const void* x16, const void* w16_packed, const float* bias, const float* gamma, const float* beta,
+                      void* out16, int n_img, int H, int W, int Cin, int Cout, int kind, int swish, void* gn_scratch,
+                      int* gn_err, void* stream);
 /* weight fp32 [Cout,Cin,kh,kw] (torch layout) -> packed fp16 rows for rgm_conv_f16; cin_pad >= Cin (multiple of 64),
  * cout_pad >= Cout. Output size: kind 0: cout_pad*cin_pad; kind 1, 3: cout_pad*9*cin_pad; kind 2: 4*cout_pad*4*cin_pad */
 int rgm_pack_conv_weight(const float* w32, void* w16_packed, int Cout, int Cin, int cout_pad, int cin_pad, int kind,

@@ -70,6 +70,7 @@ _SIGNATURES = {
     "rgm_dit_forward": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p],
     "rgm_vae_create": [_HP, c_int, ctypes.POINTER(c_int), c_int, c_int, c_int, c_int],
     "rgm_vae_destroy": [c_void_p],
+    "rgm_vae_gn_timeouts": [c_void_p],
     "rgm_vae_set_lanes": [c_void_p, c_int],
     "rgm_vae_load": [c_void_p, c_char_p, c_void_p, c_ll, c_void_p],
     "rgm_vae_encode": [c_void_p, c_void_p, c_void_p, c_int, c_void_p],
@@ -86,6 +87,8 @@ _SIGNATURES = {
     "rgm_gn_apply_f16": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
     "rgm_conv_gn_f16": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
                         c_void_p, c_void_p],
+    "rgm_conv_norm_f16": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
+                          c_int, c_int, c_void_p, c_void_p, c_void_p],
     "rgm_pack_conv_weight": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p],
     "rgm_attention_f16": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p],
 }

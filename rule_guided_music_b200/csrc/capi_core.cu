@@ -274,6 +274,45 @@ int rgm_conv_gn_f16(const void* x16_raw, const float* ab_in, const void* w16_pac
   return 0;
 }
 
+int rgm_conv_norm_f16(const void* x16, const void* w16_packed, const float* bias, const float* gamma, const float* beta,
+                      void* out16, int n_img, int H, int W, int Cin, int Cout, int kind, int swish, void* gn_scratch,
+                      int* gn_err, void* stream) {
+  if (rgm_check_device()) return -1;
+  if (!x16 || !w16_packed || !gamma || !beta || !out16 || !gn_scratch || !gn_err)
+    return set_error("rgm_conv_norm_f16: null argument");
+  GemmDesc d;
+  d.A = static_cast<const __half*>(x16);
+  d.n_img = n_img;
+  d.H = H;
+  d.W = W;
+  d.C = Cin;
+  d.lda = Cin;
+  d.B = static_cast<const __half*>(w16_packed);
+  d.N = Cout;
+  d.rows_b = Cout;
+  d.conv = kind;
+  d.epi = EPI_F16;
+  d.e.ldo = Cout;
+  d.e.bias = bias;
+  d.e.alpha = 1.f;
+  if (!gemm_gn_fuse_supported(d))
+    return set_error("rgm_conv_norm_f16: needs a 3x3 / 1x1 conv with 128 / 256 / 512 output features on images of a multiple "
+                     "of 256 pixels that span no more tiles than there are resident CTAs");
+  d.e.out = out16;
+  d.e.gn_sums = static_cast<unsigned long long*>(gn_scratch);
+  d.e.gn_gamma = gamma;
+  d.e.gn_beta = beta;
+  d.e.gn_eps = 1e-6f;
+  d.e.gn_swish = swish;
+  d.e.gn_err = gn_err;
+  if (const char* tr = getenv("RGM_DEBUG_TRACE_PTR")) d.trace = reinterpret_cast<unsigned long long*>(strtoull(tr, nullptr, 0));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  RGM_CUDA_OK(cudaMemsetAsync(gn_scratch, 0, gn_scratch_bytes(n_img), st));
+  std::string err;
+  if (launch_gemm(d, st, &err) != cudaSuccess) return set_error(err);
+  return 0;
+}
+
 int rgm_pack_conv_weight(const float* w32, void* w16_packed, int Cout, int Cin, int cout_pad, int cin_pad, int kind,
                          void* stream) {
   if (rgm_check_device()) return -1;

@@ -44,10 +44,20 @@ bool conv_gn_shape_ok(const GemmDesc& d);
 bool conv_gn_supported(const GemmDesc& d);
 cudaError_t launch_conv_gn(const GemmDesc& d, const float2* in_ab, cudaStream_t stream, std::string* err = nullptr);
 
+// Whether launch_gemm can apply GroupNorm (+ swish) to this layer's own output inside the epilogue (EpiParams::gn_sums
+// etc., gemm_tc.cuh gn_epilogue_loop): 3x3 / 1x1 convolution, 128 / 256 / 512 features, images of a multiple of 256
+// pixels spanning no more tiles than there are co-resident CTAs.  d.e needs no output / statistics pointers for the test.
+bool gemm_gn_fuse_supported(const GemmDesc& d);
+// Scratch such a launch needs, zeroed before it: per image 32 groups x 2 accumulator words (EpiParams::gn_sums).
+inline size_t gn_scratch_bytes(int n_img) { return (size_t)n_img * 512; }
+
 // number of kernels this translation unit has launched since process start (bench.py's gpu_launches claim)
 unsigned long long gemm_launch_count();
 
 int device_sm_count();
+
+// CTAs (pair = false) or CTA pairs (pair = true) of the feature-major EPI_F16 kernels co-resident on the current device
+int gemm_resident_units(bool pair);
 
 // fp32 [Cout,Cin,kh,kw] -> packed fp16 rows (capi_core.cu)
 cudaError_t launch_pack_conv_weight(const float* w32, __half* w16, int Cout, int Cin, int cout_pad, int cin_pad,

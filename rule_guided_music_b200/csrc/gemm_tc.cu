@@ -146,7 +146,57 @@ bool pair_mode_enabled() {
   return v != 0;
 }
 
+// CTAs (single-CTA kernel) / CTA pairs (pair kernel) of the EPI_F16 feature-major kernels that are co-resident on the
+// current device: the GroupNorm-in-epilogue convolutions wait on each other's tiles, so their grid must not exceed it
+// (a pair needs two free SMs of one TPC; a GPC with an odd SM count leaves one SM without a partner).
+int resident_units(bool pair) {
+  static std::atomic<int> cache[64][2];
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) dev = 63;
+  int v = cache[dev][pair ? 1 : 0].load(std::memory_order_relaxed);
+  if (v > 0) return v;
+  int sms = 0;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (pair) {
+    auto kern = gemm_sw2_kernel<EPI_F16>;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SW2_SMEM_BYTES);
+    cudaLaunchConfig_t cfg;
+    std::memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(2 * (sms / 2), 1, 1);
+    cfg.blockDim = dim3(GEMM_THREADS, 1, 1);
+    cfg.dynamicSmemBytes = SW2_SMEM_BYTES;
+    cudaLaunchAttribute at;
+    at.id = cudaLaunchAttributeClusterDimension;
+    at.val.clusterDim.x = 2;
+    at.val.clusterDim.y = 1;
+    at.val.clusterDim.z = 1;
+    cfg.attrs = &at;
+    cfg.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess || n <= 0) {
+      cudaGetLastError();
+      n = sms / 2 - 8;  // conservative: one pair lost per GPC
+    }
+    v = n < sms / 2 ? n : sms / 2;
+  } else {
+    auto kern = gemm_sw_kernel<EPI_F16>;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SW_SMEM_BYTES);
+    int n = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, GEMM_THREADS, SW_SMEM_BYTES) != cudaSuccess || n <= 0) {
+      cudaGetLastError();
+      n = 1;
+    }
+    v = sms;  // one CTA per SM is all the persistent kernel launches
+  }
+  if (v < 1) v = 1;
+  if (dev != 63) cache[dev][pair ? 1 : 0].store(v, std::memory_order_relaxed);
+  return v;
+}
+
 }  // namespace
+
+int gemm_resident_units(bool pair) { return resident_units(pair); }
 
 unsigned long long gemm_launch_count() { return g_launches.load(); }
 
@@ -297,6 +347,38 @@ cudaError_t launch_gemm(const GemmDesc& d, cudaStream_t stream, std::string* err
     grid = 2 * (int)(total < max_pairs ? total : max_pairs);
   }
   if (grid <= 0) return cudaSuccess;
+  const bool gn_fuse = d.e.gn_sums != nullptr;
+  if (gn_fuse) {
+    // GroupNorm inside the epilogue (gn_epilogue_loop): whole 256-row tiles of one image, statically assigned tiles,
+    // every CTA of the grid resident, an image's tiles within one grid-stride of each other
+    if (!sw || d.epi != EPI_F16 || p.num_par != 1 || down || d.e.resid != nullptr || d.e.addtab != nullptr || d.e.up2 ||
+        d.e.act != ACT_NONE || d.e.gn_sums == nullptr || d.e.gn_gamma == nullptr || d.e.gn_beta == nullptr ||
+        d.e.gn_err == nullptr || d.b_batch > 1)
+      return fail("gemm: this layer cannot normalise its output in the epilogue");
+    if ((oH * oW) % SW_ROWS != 0 || p.M % SW_ROWS != 0 || (d.N != 128 && d.N != 256 && d.N != 512))
+      return fail("gemm: GroupNorm in the epilogue needs images of a multiple of 256 pixels and 128 / 256 / 512 features");
+    const int units = resident_units(pair);
+    if (pair) grid = 2 * (int)(total < units ? total : units);
+    else grid = (int)(total < units ? total : units);
+    const int span = p.tiles_per_img * (pair ? (p.num_n_tiles + 1) / 2 : p.num_n_tiles);
+    if (span > (pair ? grid / 2 : grid)) return fail("gemm: an image spans more tiles than there are resident CTAs");
+    // Whole images per wave: with a grid that is a multiple of an image's tile count no image straddles two waves.  A
+    // straddling image makes its first-wave CTAs wait a whole tile time for the others' next tile, and with only two
+    // accumulator buffers that stalls their MMAs for the length of the second pass, wave after wave (measured: 0.92 ms
+    // instead of 0.56 ms per 128 -> 128 @ 128x128 launch).  The idle CTAs (20 of 148 at 64 tiles per image) cost less:
+    // the part runs at its power cap, and fewer active SMs clock higher.
+    static const int align = [] {
+      const char* e = getenv("RGM_GN_ALIGN");
+      return e ? atoi(e) : 1;
+    }();
+    if (align) {
+      int g = pair ? grid / 2 : grid;
+      g = (g / span) * span;
+      grid = pair ? 2 * g : g;
+    }
+    p.band_n = 0;
+    p.epi.gn_inv_count = 1.0f / ((float)(oH * oW) * (float)(d.N / 32));
+  }
 
   // profiling label: conv kind, K, N and epilogue identify the layer family; flops_alg counts the reference's
   // arithmetic (a 3x3 conv on the upsampled image for CONV_UP2), flops_exec what this kernel executes
@@ -306,8 +388,8 @@ cudaError_t launch_gemm(const GemmDesc& d, cudaStream_t stream, std::string* err
   const double f_exec = 2.0 * rows * d.N * Kexec;
   const double f_alg = d.conv == CONV_UP2 ? 2.0 * rows * d.N * 9.0 * d.C : f_exec;
   if (g_prof_on.load(std::memory_order_relaxed))
-    snprintf(pname, sizeof pname, "gemm_tc conv%d H%d K%d N%d epi%d %s", d.conv, d.H, (int)Kexec, d.N, d.epi,
-             pair ? "f256xr256 pair" : (sw ? "f128xr256" : "r128xf32"));
+    snprintf(pname, sizeof pname, "gemm_tc conv%d H%d K%d N%d epi%d %s%s", d.conv, d.H, (int)Kexec, d.N, d.epi,
+             pair ? "f256xr256 pair" : (sw ? "f128xr256" : "r128xf32"), gn_fuse ? " +norm" : "");
   ProfScope prof(pname, f_alg, f_exec, 0.0, stream);
 
   cudaError_t st = cudaErrorInvalidValue;
@@ -335,6 +417,26 @@ cudaError_t launch_gemm(const GemmDesc& d, cudaStream_t stream, std::string* err
   }
   if (st != cudaSuccess && err) *err = std::string("gemm launch: ") + cudaGetErrorString(st);
   return st;
+}
+
+// Layers whose epilogue can normalise their own output (gn_epilogue_loop); the same geometry as launch_gemm.
+bool gemm_gn_fuse_supported(const GemmDesc& d) {
+  if (d.conv != CONV_3x3 && d.conv != CONV_1x1) return false;
+  // 32 groups of 4, 8 or 16 channels: whole channel quads per group, groups inside one warp's 32 features
+  if (d.epi != EPI_F16 || (d.N != 128 && d.N != 256 && d.N != 512) || d.b_batch > 1 || d.block_n == 32) return false;
+  if (d.e.resid != nullptr || d.e.addtab != nullptr || d.e.up2 || d.e.act != ACT_NONE) return false;
+  if (d.H < 2 || d.W > SW_ROWS || SW_ROWS % d.W != 0) return false;
+  const long long HW = (long long)d.H * d.W;
+  if (HW % SW_ROWS != 0) return false;
+  const int tiles_per_img = (int)(HW / SW_ROWS), n_tiles = d.N / SW_FEATS;
+  const long long num_m = (long long)d.n_img * tiles_per_img;
+  const long long pair_tiles = num_m * ((n_tiles + 1) / 2);
+  const bool pair = pair_mode_enabled() && n_tiles >= 2 && pair_tiles >= device_sm_count() / 2;
+  const long long total = pair ? pair_tiles : num_m * n_tiles;
+  const int units = resident_units(pair);
+  const long long g = total < units ? total : units;
+  const int span = tiles_per_img * (pair ? (n_tiles + 1) / 2 : n_tiles);
+  return span <= g;
 }
 
 // shape test: layers the fused kernel can run

@@ -56,6 +56,18 @@ struct EpiParams {
   // optional GroupNorm partial statistics of the fp16 values just stored (EPI_F16, feature-major kernel):
   // gn_part[par * ceil(M/128) + row / 128][N / 4] = (sum, sumsq) over 128 rows x 4 channels
   float* gn_part;
+  // GroupNorm (+ swish) of this convolution's OWN output applied inside the epilogue (feature-major kernels, EPI_F16,
+  // gn_epilogue_loop): when gn_sums != nullptr `out` receives swish(GroupNorm(conv(x))) and the raw tensor is never
+  // written.  gn_sums: per-(image, group) accumulators [image][32][2] -- fixed-point sum / sum of squares in bits 63..8,
+  // arrivals in bits 7..0 -- zeroed before the launch; gn_inv_count = 1 / (pixels x channels per group); gn_gamma /
+  // gn_beta: the norm's affine [N]; gn_err: set to 1 if a wait gives up (never in a healthy run)
+  unsigned long long* gn_sums;
+  float gn_inv_count;
+  const float* gn_gamma;
+  const float* gn_beta;
+  float gn_eps;
+  int gn_swish;
+  int* gn_err;
 };
 
 struct GemmParams {
@@ -706,6 +718,185 @@ __device__ __forceinline__ void sw_epilogue_tile(const GemmParams& p, uint32_t t
   }
 }
 
+// GroupNorm (+ swish) of the convolution's own output INSIDE its epilogue -- the normalise pass over the tensor
+// (taming/modules/diffusionmodules/model.py:117-137: h = conv2(swish(norm2(conv1(...))))) never touches HBM.
+//
+// GroupNorm needs statistics over a whole image, i.e. over the tiles of up to 64 other CTAs, so the accumulator WAITS IN
+// TENSOR MEMORY for them: (1) a first pass over the tile's TMEM columns takes the fp32 sums of this warp's 32 features x
+// 128 rows and adds them, as fixed-point integers that also count arrivals, to the image's per-group accumulators;
+// (2) the lanes poll their group's words until the image's other row tiles have contributed -- meanwhile the MMA warp is
+// filling the second accumulator buffer with the next tile; (3) the totals give the affine (integer sums: deterministic
+// whatever the arrival order); (4) a second pass over the same TMEM columns stores swish(a x + b) as fp16.  The raw convolution output is never written and never re-read:
+// per element one 2-byte store instead of store + load + store.
+//
+// Progress: tiles are statically assigned (tile t -> CTA t mod grid), the host launches no more CTAs than are
+// co-resident and only layers whose images span at most `grid` consecutive tiles, so two tiles of one image never sit on
+// the same CTA and every wait is for tiles of the current or an earlier wave of other, running CTAs.  A wait that lasts
+// ~1 s gives up and raises gn_err instead of hanging the device.
+template <int LDO>
+__device__ __forceinline__ void gn_store_cols(const uint32_t (&r)[32], __half* op, int ldo_dyn, float alpha, float bias,
+                                              float a, float b, bool swish) {
+  const int ldo = LDO > 0 ? LDO : ldo_dyn;
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    float y = fmaf(a, fmaf(__uint_as_float(r[j]), alpha, bias), b);
+    if (swish) y = silu_f(y);
+    op[j * ldo] = __float2half_rn(y);
+  }
+}
+
+// first pass: statistics of this warp's 32 features x 128 rows, published to the image's accumulators
+__device__ __forceinline__ void gn_pass1(const GemmParams& p, uint32_t tmem_acc, int m_tile, int n_tile, int quad,
+                                         int rhalf, int lane, unsigned long long* tr) {  // tr: trace slots 4, 6
+  const EpiParams& e = p.epi;
+  if (tr && lane == 0) tr[4] = clock64();
+  const uint32_t taddr = tmem_acc + (static_cast<uint32_t>(quad * 32) << 16) + rhalf * 128;
+  const int n = n_tile * SW_FEATS + quad * 32 + lane;  // this thread's output feature
+  const float bias = e.bias ? __ldg(e.bias + n) : 0.f;
+  float gs = 0.f, gq = 0.f;  // from the fp32 values (the host guarantees M % 256 == 0: every row is valid)
+#pragma unroll 1
+  for (int c = 0; c < 128; c += 32) {
+    uint32_t r[32];
+    tmem_ld_32x32(taddr + c, r);
+    tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const float x = fmaf(__uint_as_float(r[j]), e.alpha, bias);
+      gs += x;
+      gq = fmaf(x, x, gq);
+    }
+  }
+  // sums over this warp's channels of each GroupNorm group (4, 8 or 16 consecutive lanes)
+  const int cpg = p.N >> 5;  // channels per group (32 groups)
+  for (int o = 1; o < cpg; o <<= 1) {
+    gs += __shfl_xor_sync(0xffffffffu, gs, o);
+    gq += __shfl_xor_sync(0xffffffffu, gq, o);
+  }
+  // Each (image, group) owns two 64-bit words: bits 63..8 accumulate the sum (sum of squares) as a 36.20 FIXED-POINT
+  // integer, bits 7..0 count the contributions.  One atomic add delivers a warp's partial AND its arrival, so no fence
+  // has to order data before a flag (a release cost ~3 K cycles per tile here), and integer addition is associative:
+  // the totals -- and the whole decode -- are bit-identical whatever order the CTAs arrive in.
+  const int img = m_tile / p.tiles_per_img;
+  unsigned long long* gsum = e.gn_sums + ((long long)img * 32 + n / cpg) * 2;
+  if ((lane & (cpg - 1)) == 0) {
+    atomicAdd(gsum, ((unsigned long long)__double2ll_rn((double)gs * 1048576.0) << 8) + 1ull);
+    atomicAdd(gsum + 1, ((unsigned long long)__double2ll_rn((double)gq * 1048576.0) << 8) + 1ull);
+  }
+  if (tr && lane == 0) tr[6] = clock64();  // statistics published
+}
+
+// whether the image's other row tiles have contributed to this lane's group (a word is complete when its count reaches
+// the image's row tiles x 2, at most 128 < 256); warp-uniform result, the words in w0 / w1
+__device__ __forceinline__ bool gn_ready(const GemmParams& p, int m_tile, int n_tile, int quad, int lane,
+                                         unsigned long long& w0, unsigned long long& w1) {
+  const EpiParams& e = p.epi;
+  const int n = n_tile * SW_FEATS + quad * 32 + lane;
+  const int img = m_tile / p.tiles_per_img;
+  const unsigned spi = (unsigned)p.tiles_per_img * 2u;
+  const unsigned long long* gsum = e.gn_sums + ((long long)img * 32 + n / (p.N >> 5)) * 2;
+  w0 = ld_relaxed_gpu_u64(gsum);
+  w1 = ld_relaxed_gpu_u64(gsum + 1);
+  const bool done = (((unsigned)w0 & 255u) == spi && ((unsigned)w1 & 255u) == spi) || (p.debug & 16);
+  return __all_sync(0xffffffffu, done);
+}
+
+// second pass: normalise + activate + store from the same TMEM columns, given the group's complete totals
+__device__ __forceinline__ void gn_pass2(const GemmParams& p, uint32_t tmem_acc, int m_tile, int n_tile, int quad,
+                                         int rhalf, int lane, unsigned long long w0, unsigned long long w1,
+                                         unsigned long long* tr) {  // tr: trace slots 7, 5
+  const EpiParams& e = p.epi;
+  const uint32_t taddr = tmem_acc + (static_cast<uint32_t>(quad * 32) << 16) + rhalf * 128;
+  const int n = n_tile * SW_FEATS + quad * 32 + lane;
+  const float bias = e.bias ? __ldg(e.bias + n) : 0.f;
+  const float gamma = __ldg(e.gn_gamma + n), beta = __ldg(e.gn_beta + n);
+  const int rbase = m_tile * SW_ROWS + rhalf * 128;
+  if (tr && lane == 0) tr[7] = clock64();  // the image's statistics are complete
+  float a, b;
+  {
+    const double s = (double)((long long)w0 >> 8) * (1.0 / 1048576.0);
+    const double q = (double)((long long)w1 >> 8) * (1.0 / 1048576.0);
+    const double inv = (double)e.gn_inv_count;  // 1 / (pixels x channels per group)
+    const double mean = s * inv;
+    const double var = q * inv - mean * mean;
+    const float rstd = rsqrtf(fmaxf((float)var, 0.f) + e.gn_eps);
+    a = rstd * gamma;
+    b = beta - (float)mean * a;
+  }
+  __half* op = static_cast<__half*>(e.out) + (long long)rbase * e.ldo + n;
+  const bool sw = e.gn_swish != 0;
+#pragma unroll 1
+  for (int c = 0; c < 128; c += 32) {
+    uint32_t r[32];
+    tmem_ld_32x32(taddr + c, r);
+    tmem_ld_wait();
+    __half* oc = op + (long long)c * e.ldo;
+    switch (e.ldo) {
+      case 128: gn_store_cols<128>(r, oc, e.ldo, e.alpha, bias, a, b, sw); break;
+      case 256: gn_store_cols<256>(r, oc, e.ldo, e.alpha, bias, a, b, sw); break;
+      case 512: gn_store_cols<512>(r, oc, e.ldo, e.alpha, bias, a, b, sw); break;
+      default: gn_store_cols<0>(r, oc, e.ldo, e.alpha, bias, a, b, sw); break;
+    }
+  }
+  if (tr && lane == 0) tr[5] = clock64();
+}
+
+// The epilogue warps' tile loop of a GroupNorm-in-epilogue launch.  While a tile waits for its image's statistics the
+// warps are idle (3-5 K cycles of other CTAs' skew), so the wait is OPPORTUNISTICALLY filled with the first pass of the
+// next tile when that tile's accumulator is already complete (the epilogue-bound case: first pass 2 K + second pass 8 K
+// cycles against the 12 K-cycle mainloop of the K = 1152 convolutions); when the MMAs are the bottleneck the next
+// accumulator is not ready and nothing is reordered.  Tile k of this CTA lives in accumulator buffer k & 1.
+// coords(t, m_tile, n_tile) maps a tile index; release(acc) frees a buffer.
+template <class Coords, class Release>
+__device__ __forceinline__ void gn_epilogue_loop(const GemmParams& p, uint32_t tmem_base, uint64_t* tmem_full, int first,
+                                                 int stride, int total, int quad, int rhalf, int lane, bool tracer,
+                                                 Coords coords, Release release) {
+  int k = 0, m_tile = 0, n_tile = 0;
+  int t = first;
+  if (t >= total) return;
+  unsigned long long* trace = (tracer && p.trace) ? p.trace : nullptr;
+  coords(t, m_tile, n_tile);
+  mbar_wait(&tmem_full[0], 0);
+  tc_fence_after();
+  gn_pass1(p, tmem_base, m_tile, n_tile, quad, rhalf, lane, trace);
+  for (;;) {
+    const int tn = t + stride, kn = k + 1;
+    int m_next = 0, n_next = 0;
+    bool next_done = tn >= total;  // nothing to pull forward after the last tile
+    if (!next_done) coords(tn, m_next, n_next);
+    unsigned long long w0, w1;
+    const long long t0 = clock64();
+    while (!gn_ready(p, m_tile, n_tile, quad, lane, w0, w1)) {
+      if (!next_done) {
+        const uint32_t ok = mbar_test(&tmem_full[kn & 1], (kn >> 1) & 1);
+        if (__all_sync(0xffffffffu, ok != 0)) {
+          tc_fence_after();
+          gn_pass1(p, tmem_base + (kn & 1) * SW_ROWS, m_next, n_next, quad, rhalf, lane, trace ? trace + kn * 8 : nullptr);
+          next_done = true;
+          continue;
+        }
+      }
+      if (clock64() - t0 > (1LL << 31)) {  // ~1 s: give up instead of hanging the device
+        *p.epi.gn_err = 1;
+        break;
+      }
+    }
+    gn_pass2(p, tmem_base + (k & 1) * SW_ROWS, m_tile, n_tile, quad, rhalf, lane, w0, w1, trace ? trace + k * 8 : nullptr);
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) release(k & 1);
+    if (tn >= total) break;
+    if (!next_done) {
+      mbar_wait(&tmem_full[kn & 1], (kn >> 1) & 1);
+      tc_fence_after();
+      gn_pass1(p, tmem_base + (kn & 1) * SW_ROWS, m_next, n_next, quad, rhalf, lane, trace ? trace + kn * 8 : nullptr);
+    }
+    t = tn;
+    m_tile = m_next;
+    n_tile = n_next;
+    ++k;
+  }
+}
+
 template <int EPI>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_sw_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
@@ -823,6 +1014,15 @@ gemm_sw_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
     const int rhalf = ew >> 2;   // which 128 of the tile's 256 rows
     int acc = 0;
     uint32_t acc_phase = 0;
+    if (EPI == EPI_F16 && p.epi.gn_sums != nullptr) {  // (num_par == 1 in this mode)
+      gn_epilogue_loop(
+          p, tmem_base, tmem_full, blockIdx.x, gridDim.x, total_tiles, quad, rhalf, lane, blockIdx.x == 0 && warp == 2,
+          [&](int t, int& m_tile, int& n_tile) {
+            m_tile = t / p.num_n_tiles;
+            n_tile = t - m_tile * p.num_n_tiles;
+          },
+          [&](int a) { mbar_arrive(&tmem_empty[a]); });
+    } else
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
       int par, tt;
       split_parity(t, p.num_par, tiles_mn, p.par_fast != 0, par, tt);
@@ -1017,6 +1217,19 @@ gemm_sw2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
     const int rhalf = ew >> 2;
     int acc = 0;
     uint32_t acc_phase = 0;
+    if (EPI == EPI_F16 && p.epi.gn_sums != nullptr) {  // (num_par == 1, an even number of feature tiles in this mode)
+      gn_epilogue_loop(
+          p, tmem_base, tmem_full, pair_id, num_pairs, total_tiles, quad, rhalf, lane, blockIdx.x == 0 && warp == 2,
+          [&](int t, int& m_tile, int& n_tile) {
+            int n_pair;
+            sw2_tile_coords(t, p.num_m_tiles, pairs_n, p.band_n, m_tile, n_pair);
+            n_tile = 2 * n_pair + (int)rank;
+          },
+          [&](int a) {
+            if (rank == 0) mbar_arrive(&tmem_empty[a]);
+            else mbar_arrive_remote(&tmem_empty[a], 0);
+          });
+    } else
     for (int t = pair_id; t < total_tiles; t += num_pairs) {
       int par, tt;
       split_parity(t, p.num_par, tiles_mn, p.par_fast != 0, par, tt);
@@ -1026,8 +1239,9 @@ gemm_sw2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       if (p.trace && blockIdx.x == 0 && warp == 2 && lane == 0) p.trace[(t / num_pairs) * 8 + 4] = clock64();
-      if (n_tile < p.num_n_tiles && !(p.debug & 2))
+      if (n_tile < p.num_n_tiles && !(p.debug & 2)) {
         sw_epilogue_tile<EPI>(p, tmem_base + acc * SW_ROWS, m_tile, n_tile, par, quad, rhalf, lane);
+      }
       tc_fence_before();
       __syncwarp();
       if (p.trace && blockIdx.x == 0 && warp == 2 && lane == 0) p.trace[(t / num_pairs) * 8 + 5] = clock64();

@@ -66,6 +66,20 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint64_t* bar, uint32_t parity
       : "memory");
   return ok;
 }
+// non-blocking test of a phase (try_wait may suspend the thread for a while; test_wait returns at once)
+__device__ __forceinline__ uint32_t mbar_test(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok;
+}
 // Bounded wait: a pipeline bug must trap (→ launch error the host reports) instead of hanging the GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
@@ -249,6 +263,25 @@ __device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
           smem_u32(bar)),
       "h"(static_cast<uint16_t>(3))
       : "memory");
+}
+
+// ----------------------------------------------------------------------------------------------
+// device-scope release / acquire on a global counter: the per-image arrival counters of the GroupNorm-in-epilogue
+// convolutions (gemm_tc.cuh, gn_epilogue_loop).  The releasing lane's warp-mates order their own stores before it
+// with __syncwarp (causality order is cumulative); the acquiring lane's warp-mates read after a __syncwarp.
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ void red_release_gpu_add(int* p, int v) {
+  asm volatile("red.release.gpu.global.add.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_relaxed_gpu_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
 }
 
 // ----------------------------------------------------------------------------------------------

@@ -81,12 +81,17 @@ struct Vae {
     // abbuf[2]: GroupNorm affines ping-pong -- a convolution reads its input's affine from one (fused normalise, or the
     // gn_apply pass before it) while its output's affine is written into the other
     DevBuf act[4], gnpart, abbuf[2], attn_s;
+    DevBuf gncount;  // statistics accumulators (with arrival counts) of the GroupNorm-in-epilogue convolutions
     cudaStream_t stream = nullptr;
     cudaEvent_t done = nullptr;
   } lane[2];
   cudaEvent_t fork = nullptr;
   int n_lanes = 2;
   int chunk_tiles = 128;
+  // conv1 of a ResnetBlock applies norm2 + swish to its own output inside its epilogue (gemm_tc.cuh,
+  // gn_epilogue_loop): RGM_GN_EPI=0 restores the separate normalise pass
+  bool gn_epi = true;
+  int* gn_err = nullptr;  // device flag: a GroupNorm-in-epilogue wait gave up (rgm_vae_gn_timeouts)
 
   ~Vae() {
     for (void* p : allocs) cudaFree(p);
@@ -173,6 +178,8 @@ int vae_build(Vae* m) {
                         CONV_UP2);
   }
   ok = ok && m->make_norm(m->norm_out, "decoder.norm_out", block_in);
+  m->gn_err = m->alloc<int>(1);
+  ok = ok && m->gn_err != nullptr;
   m->cout_cin = block_in;
   m->cout_w = m->alloc<float>((long long)m->out_ch * block_in * 9);
   m->cout_b = m->alloc<float>(m->out_ch);
@@ -241,8 +248,9 @@ struct Ctx {
 // them into that norm's per-(tile, channel) affine, so no statistics pass over the tensor follows.  (Folding inside the
 // epilogue -- last-arriving warp per image behind a device-scope fence -- was measured in round 2: the fences and the
 // serial fold cost 2-10x on the short-K convolutions; profiles/README.md.)
-int run_conv(Ctx& c, const Conv& cv, const __half* x, int H, const __half* resid, __half* out, const Norm* next,
-             bool fuse_input_norm = false) {
+// `out_norm` (instead of `next`): `out` receives swish(out_norm(conv(x))) -- the statistics are exchanged between the CTAs
+// of an image while the accumulators wait in tensor memory, and the raw convolution output is never written.
+GemmDesc conv_desc(const Ctx& c, const Conv& cv, const __half* x, int H, const __half* resid, __half* out) {
   GemmDesc d;
   d.A = x;
   d.n_img = c.nt;
@@ -266,9 +274,25 @@ int run_conv(Ctx& c, const Conv& cv, const __half* x, int H, const __half* resid
     d.e.upH = H;
     d.e.upW = H;
   }
+  return d;
+}
+
+int run_conv(Ctx& c, const Conv& cv, const __half* x, int H, const __half* resid, __half* out, const Norm* next,
+             bool fuse_input_norm = false, const Norm* out_norm = nullptr) {
+  GemmDesc d = conv_desc(c, cv, x, H, resid, out);
   if (next != nullptr) {
     if (next->c != cv.cout || cv.cout % 128 != 0) return set_error("rgm_vae: GroupNorm partials need a 128-multiple channel count");
     d.e.gn_part = static_cast<float*>(c.L->gnpart.p);
+  }
+  if (out_norm != nullptr) {
+    if (next != nullptr || out_norm->c != cv.cout) return set_error("rgm_vae: bad GroupNorm-in-epilogue request");
+    d.e.gn_sums = static_cast<unsigned long long*>(c.L->gncount.p);
+    d.e.gn_gamma = out_norm->gamma;
+    d.e.gn_beta = out_norm->beta;
+    d.e.gn_eps = 1e-6f;
+    d.e.gn_swish = 1;
+    d.e.gn_err = c.m->gn_err;
+    RGM_CUDA_OK(cudaMemsetAsync(c.L->gncount.p, 0, gn_scratch_bytes(c.nt), c.st));
   }
   if (fuse_input_norm) {  // x is RAW: normalise + swish with the current affine inside the operand path (conv_gn.cuh)
     std::string err;
@@ -304,6 +328,12 @@ bool can_fuse_norm(const Ctx& c, const Conv& cv, int H) {
   return conv_gn_supported(d);
 }
 
+// whether this convolution can apply the GroupNorm that consumes its output inside its own epilogue
+bool can_fuse_out_norm(const Ctx& c, const Conv& cv, int H) {
+  if (!c.m->gn_epi) return false;
+  return gemm_gn_fuse_supported(conv_desc(c, cv, nullptr, H, nullptr, nullptr));
+}
+
 // ResnetBlock (model.py:117-137). x: input [nt,H,H,cin] whose GroupNorm affine (norm1) is current in L->abbuf -- its
 // producer's epilogue put it there -- unless stats_from_tensor; t, h: scratch; out may alias neither x nor h.  `next` =
 // the norm that consumes this block's output (its affine is left current), or null.
@@ -312,20 +342,21 @@ int run_res(Ctx& c, const Res& r, const __half* x, int H, __half* t, __half* h, 
   const int HW = H * H;
   if (stats_from_tensor)  // x did not come out of a GEMM epilogue (the stems): one direct statistics pass
     RGM_CUDA_OK(launch_gn_stats(x, r.n1.gamma, r.n1.beta, c.ab(), c.nt, HW, r.n1.c, 1e-6f, c.st));
-  const bool f1 = can_fuse_norm(c, r.c1, H), f2 = can_fuse_norm(c, r.c2, H);
+  const bool e1 = can_fuse_out_norm(c, r.c1, H);  // conv1 writes swish(norm2(conv1(.))) itself: no pass over h
+  const bool f1 = can_fuse_norm(c, r.c1, H), f2 = !e1 && can_fuse_norm(c, r.c2, H);
   if (f1) {
-    if (run_conv(c, r.c1, x, H, nullptr, h, &r.n2, true)) return -1;
+    if (run_conv(c, r.c1, x, H, nullptr, h, e1 ? nullptr : &r.n2, true, e1 ? &r.n2 : nullptr)) return -1;
   } else {
     RGM_CUDA_OK(launch_gn_apply(x, c.ab(), t, c.nt, HW, r.n1.c, 1, c.st));
-    if (run_conv(c, r.c1, t, H, nullptr, h, &r.n2)) return -1;
+    if (run_conv(c, r.c1, t, H, nullptr, h, e1 ? nullptr : &r.n2, false, e1 ? &r.n2 : nullptr)) return -1;
   }
-  if (!f2) RGM_CUDA_OK(launch_gn_apply(h, c.ab(), t, c.nt, HW, r.n2.c, 1, c.st));
+  if (!f2 && !e1) RGM_CUDA_OK(launch_gn_apply(h, c.ab(), t, c.nt, HW, r.n2.c, 1, c.st));
   const __half* resid = x;
   if (r.has_nin) {
     if (run_conv(c, r.nin, x, H, nullptr, out, nullptr)) return -1;
     resid = out;  // conv2 adds the shortcut it finds in `out` and overwrites it (same thread reads then writes)
   }
-  return run_conv(c, r.c2, f2 ? h : t, H, resid, out, next, f2);
+  return run_conv(c, r.c2, (f2 || e1) ? h : t, H, resid, out, next, f2);
 }
 
 // AttnBlock (model.py:168-192) at 16x16: single head over the 256 positions of a tile.  x = buf[cur] (its GroupNorm
@@ -548,6 +579,7 @@ int vae_reserve(Vae* m, int chunk, int lanes, cudaStream_t st) {
     RGM_CUDA_OK(L.gnpart.reserve((size_t)chunk * maxc / 8 + 1024, st));
     for (int i = 0; i < 2; ++i) RGM_CUDA_OK(L.abbuf[i].reserve((size_t)chunk * 512 * sizeof(float2) * 2, st));
     RGM_CUDA_OK(L.attn_s.reserve((size_t)chunk * 256 * 256 * sizeof(float), st));
+    RGM_CUDA_OK(L.gncount.reserve(gn_scratch_bytes(chunk) + 1024, st));
   }
   return 0;
 }
@@ -584,6 +616,7 @@ int rgm_vae_create(rgm_vae** out, int ch, const int* ch_mult, int n_levels, int 
   }
   if (const char* e = getenv("RGM_VAE_CHUNK")) m->chunk_tiles = atoi(e) > 0 ? atoi(e) : m->chunk_tiles;
   if (const char* e = getenv("RGM_VAE_LANES")) m->n_lanes = atoi(e) >= 2 ? 2 : 1;
+  if (const char* e = getenv("RGM_GN_EPI")) m->gn_epi = atoi(e) != 0;
   if (vae_build(m) != 0) {
     delete m;
     return -1;
@@ -605,6 +638,16 @@ int rgm_vae_reserve(rgm_vae* h, int n_tiles) {
   const int chunk = m->chunk_tiles < n_tiles ? m->chunk_tiles : n_tiles;
   const int lanes = (m->n_lanes > 1 && n_tiles > chunk) ? 2 : 1;
   return vae_reserve(m, chunk, lanes, nullptr);
+}
+
+int rgm_vae_gn_timeouts(rgm_vae* h) {
+  if (!h) return set_error("rgm_vae_gn_timeouts: null handle");
+  Vae* m = reinterpret_cast<Vae*>(h);
+  int v = 0;
+  if (cudaDeviceSynchronize() != cudaSuccess ||
+      cudaMemcpy(&v, m->gn_err, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess)
+    return set_error("rgm_vae_gn_timeouts: device error");
+  return v;
 }
 
 int rgm_vae_destroy(rgm_vae* h) {

@@ -96,6 +96,17 @@ class AutoencoderKL:
         """2 = overlap GroupNorm passes of one tile chunk with the convolutions of the next (default), 1 = serial."""
         _lib.call("rgm_vae_set_lanes", self._h, int(lanes))
 
+    def gn_timeouts(self):
+        """Diagnostic (rgm_vae_gn_timeouts): 1 if a convolution that normalises its own output ever gave up waiting for
+        its image's other tiles -- never in a healthy run.  Synchronises the device."""
+        if self._h is None:
+            return 0
+        with torch.cuda.device(self._device):
+            rc = _lib.lib().rgm_vae_gn_timeouts(self._h)
+        if rc < 0:
+            _lib.check(rc)
+        return rc
+
     def _destroy(self):
         if self._h is not None:
             _lib.lib().rgm_vae_destroy(self._h)

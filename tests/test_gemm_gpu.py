@@ -151,3 +151,59 @@ def test_conv_with_fused_groupnorm_input(cuda, n, H, cin, resid):
     # partial sums are taken of the fp32 values before the fp16 rounding of the store: 512 roundings of 2^-11 |v| apart
     o = out.float().reshape(n * H * W // 128, 128, cout // 4, 4)
     assert torch.allclose(part[..., 0], o.sum(dim=(1, 3)), rtol=1e-4, atol=0.15)
+
+
+@pytest.mark.parametrize("n,H,cin,cout,kind,swish", [
+    (3, 32, 128, 128, 1, 1),     # single-CTA kernel, 4 tiles per image
+    (3, 128, 128, 128, 1, 1),    # 64 tiles per image, 192 tiles: the third image straddles two waves of the grid
+    (40, 16, 256, 512, 1, 1),    # CTA pairs, 2 feature pairs per image, groups of 16 channels (4 quads)
+    (10, 64, 256, 256, 1, 1),    # CTA pairs, 16 row tiles per image, groups of 8 channels; images straddle waves
+    (130, 128, 128, 128, 1, 1),  # a full bench chunk of the 128x128 level: 8320 tiles, 57 waves
+    (80, 16, 128, 256, 0, 0),    # 1x1 conv on CTA pairs, one tile per image, norm without swish
+])
+def test_conv_with_groupnorm_of_its_own_output(cuda, n, H, cin, cout, kind, swish):
+    """swish(GroupNorm(conv(x))) with the normalisation applied inside the convolution's epilogue (gemm_tc.cuh
+    gn_epilogue_loop: statistics exchanged between the CTAs of an image while the accumulators wait in tensor
+    memory) against torch fp32 on the same fp16-rounded operands, and against the two-pass form of this library
+    (rgm_conv_f16 + torch statistics + rgm_gn_apply_f16), which differs only by the fp16 rounding of the stored raw
+    tensor.  The wait must never give up."""
+    g = torch.Generator(device="cpu").manual_seed(n * 977 + H + cin + cout + kind)
+    k = 1 if kind == 0 else 3
+    x = (torch.randn(n, H, H, cin, generator=g) * 1.3 + 0.2).to(cuda).half()
+    w = (torch.randn(cout, cin, k, k, generator=g) / (cin * k * k) ** 0.5).to(cuda)
+    bias = torch.randn(cout, generator=g).to(cuda)
+    gamma = (torch.rand(cout, generator=g) + 0.5).to(cuda)
+    beta = (torch.randn(cout, generator=g) * 0.3).to(cuda)
+    wp = _pack(w, kind)
+    scratch = torch.full((n * 128,), 12345, device=cuda, dtype=torch.int32)  # n * 512 bytes; the call must zero it
+    err = torch.zeros(1, device=cuda, dtype=torch.int32)
+    out = torch.empty(n, H, H, cout, device=cuda, dtype=torch.float16)
+    for _ in range(2):  # twice: accumulators and counters are re-armed by every call
+        _lib.call("rgm_conv_norm_f16", _lib.ptr(x), _lib.ptr(wp), _lib.ptr(bias), _lib.ptr(gamma), _lib.ptr(beta),
+                  _lib.ptr(out), n, H, H, cin, cout, kind, swish, _lib.ptr(scratch), _lib.ptr(err), _lib.stream_ptr())
+    torch.cuda.synchronize()
+    assert err.item() == 0, "a GroupNorm-in-epilogue wait gave up"
+    count = scratch.view(n, 64, 2)[:, :, 0] & 255   # low byte of every accumulator word = contributions received
+    assert int(count.min()) == int(count.max()) == 2 * (H * H // 256)
+    conv = F.conv2d(x.float().permute(0, 3, 1, 2), w.half().float(), bias, padding=k // 2)
+    ref = F.group_norm(conv, 32, gamma, beta, eps=1e-6)
+    if swish:
+        ref = F.silu(ref)
+    ref = ref.permute(0, 2, 3, 1)
+    e = (out.float() - ref).abs().max().item()
+    assert e <= 2e-3 * ref.abs().max().item() + 1e-3, e
+    assert torch.isfinite(out.float()).all()
+    # the two-pass form: raw fp16 tensor, statistics of the fp32 result, normalise pass
+    raw = _conv(x, wp, bias, cout, kind)
+    cpg = cout // 32
+    c32 = conv.permute(0, 2, 3, 1).reshape(n, H * H, 32, cpg)
+    mean = c32.mean(dim=(1, 3))
+    rstd = (c32.var(dim=(1, 3), unbiased=False) + 1e-6).rsqrt()
+    a = rstd.repeat_interleave(cpg, dim=1) * gamma
+    b = beta - mean.repeat_interleave(cpg, dim=1) * a
+    ab = torch.stack((a, b), dim=-1).contiguous()
+    two = torch.empty_like(out)
+    _lib.call("rgm_gn_apply_f16", _lib.ptr(raw), _lib.ptr(ab), _lib.ptr(two), n, H * H, cout, swish, _lib.stream_ptr())
+    torch.cuda.synchronize()
+    d = (out.float() - two.float()).abs().max().item()
+    assert d <= 4e-3 * two.float().abs().max().item() + 1e-3, d

@@ -206,10 +206,14 @@ int rgm_conv_gn_f16(const void* x16_raw, const float* ab_in, const void* w16_pac
  * partial statistics while the accumulators wait in tensor memory, so the raw output is never written.  kind 0 / 1,
  * Cout in {128, 256, 512}, H*W a multiple of 256; gamma / beta f32 [Cout]; gn_scratch: n * 512 bytes of device
  * scratch (per-group statistics accumulators that also count arrivals, zeroed by the call); gn_err: device int that is set to 1
- * if a wait gives up (never in a healthy run).  swish = 0 applies the norm only. */
+ * if a wait gives up (never in a healthy run).  swish = 0 applies the norm only.
+ * raw16 == NULL: only out16 = swish(norm(conv(x))) is written (the accumulators wait in tensor memory for the statistics).
+ * raw16 != NULL ("dual" form, model.py:117-137 where a block's output feeds both the next shortcut and the next norm1):
+ * raw16 = conv(x) + resid16 (resid16 may be NULL, or alias raw16) and out16 = swish(norm(raw16)), the normalised copy
+ * written one tile later from the warp's own L2-resident rows. */
 int rgm_conv_norm_f16(const void* x16, const void* w16_packed, const float* bias, const float* gamma, const float* beta,
-                      void* out16, int n_img, int H, int W, int Cin, int Cout, int kind, int swish, void* gn_scratch,
-                      int* gn_err, void* stream);
+                      const void* resid16, void* raw16, void* out16, int n_img, int H, int W, int Cin, int Cout, int kind,
+                      int swish, void* gn_scratch, int* gn_err, void* stream);
 /* weight fp32 [Cout,Cin,kh,kw] (torch layout) -> packed fp16 rows for rgm_conv_f16; cin_pad >= Cin (multiple of 64),
  * cout_pad >= Cout. Output size: kind 0: cout_pad*cin_pad; kind 1, 3: cout_pad*9*cin_pad; kind 2: 4*cout_pad*4*cin_pad */
 int rgm_pack_conv_weight(const float* w32, void* w16_packed, int Cout, int Cin, int cout_pad, int cin_pad, int kind,

@@ -275,8 +275,8 @@ int rgm_conv_gn_f16(const void* x16_raw, const float* ab_in, const void* w16_pac
 }
 
 int rgm_conv_norm_f16(const void* x16, const void* w16_packed, const float* bias, const float* gamma, const float* beta,
-                      void* out16, int n_img, int H, int W, int Cin, int Cout, int kind, int swish, void* gn_scratch,
-                      int* gn_err, void* stream) {
+                      const void* resid16, void* raw16, void* out16, int n_img, int H, int W, int Cin, int Cout, int kind,
+                      int swish, void* gn_scratch, int* gn_err, void* stream) {
   if (rgm_check_device()) return -1;
   if (!x16 || !w16_packed || !gamma || !beta || !out16 || !gn_scratch || !gn_err)
     return set_error("rgm_conv_norm_f16: null argument");
@@ -298,7 +298,16 @@ int rgm_conv_norm_f16(const void* x16, const void* w16_packed, const float* bias
   if (!gemm_gn_fuse_supported(d))
     return set_error("rgm_conv_norm_f16: needs a 3x3 / 1x1 conv with 128 / 256 / 512 output features on images of a multiple "
                      "of 256 pixels that span no more tiles than there are resident CTAs");
-  d.e.out = out16;
+  if (resid16 != nullptr && raw16 == nullptr)
+    return set_error("rgm_conv_norm_f16: a residual needs raw16 (the raw tensor is what the residual is added to)");
+  if (raw16 != nullptr) {  // dual form: raw tensor (+ residual) and its normalised copy
+    d.e.out = raw16;
+    d.e.gn_out2 = static_cast<__half*>(out16);
+    d.e.resid = static_cast<const __half*>(resid16);
+    d.e.ldr = Cout;
+  } else {
+    d.e.out = out16;
+  }
   d.e.gn_sums = static_cast<unsigned long long*>(gn_scratch);
   d.e.gn_gamma = gamma;
   d.e.gn_beta = beta;

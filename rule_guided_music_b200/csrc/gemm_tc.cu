@@ -351,7 +351,8 @@ cudaError_t launch_gemm(const GemmDesc& d, cudaStream_t stream, std::string* err
   if (gn_fuse) {
     // GroupNorm inside the epilogue (gn_epilogue_loop): whole 256-row tiles of one image, statically assigned tiles,
     // every CTA of the grid resident, an image's tiles within one grid-stride of each other
-    if (!sw || d.epi != EPI_F16 || p.num_par != 1 || down || d.e.resid != nullptr || d.e.addtab != nullptr || d.e.up2 ||
+    if (!sw || d.epi != EPI_F16 || p.num_par != 1 || down || (d.e.resid != nullptr && d.e.gn_out2 == nullptr) ||
+        (d.e.resid != nullptr && d.e.ldr != d.e.ldo) || d.e.addtab != nullptr || d.e.up2 ||
         d.e.act != ACT_NONE || d.e.gn_sums == nullptr || d.e.gn_gamma == nullptr || d.e.gn_beta == nullptr ||
         d.e.gn_err == nullptr || d.b_batch > 1)
       return fail("gemm: this layer cannot normalise its output in the epilogue");
@@ -362,14 +363,12 @@ cudaError_t launch_gemm(const GemmDesc& d, cudaStream_t stream, std::string* err
     else grid = (int)(total < units ? total : units);
     const int span = p.tiles_per_img * (pair ? (p.num_n_tiles + 1) / 2 : p.num_n_tiles);
     if (span > (pair ? grid / 2 : grid)) return fail("gemm: an image spans more tiles than there are resident CTAs");
-    // Whole images per wave: with a grid that is a multiple of an image's tile count no image straddles two waves.  A
-    // straddling image makes its first-wave CTAs wait a whole tile time for the others' next tile, and with only two
-    // accumulator buffers that stalls their MMAs for the length of the second pass, wave after wave (measured: 0.92 ms
-    // instead of 0.56 ms per 128 -> 128 @ 128x128 launch).  The idle CTAs (20 of 148 at 64 tiles per image) cost less:
-    // the part runs at its power cap, and fewer active SMs clock higher.
+    // RGM_GN_ALIGN=1 rounds the grid down to whole images per wave (no image straddles two waves of the grid).  Measured
+    // (profiles/r2_trace_conv_norm.txt): not worth the idle CTAs -- 0.599 vs 0.597 ms at 128 -> 128 @ 128x128 (128 of
+    // 148 CTAs), 0.499 vs 0.474 ms at 256 -> 256 @ 64x64 (64 of 74 pairs) -- so it is off.
     static const int align = [] {
       const char* e = getenv("RGM_GN_ALIGN");
-      return e ? atoi(e) : 1;
+      return e ? atoi(e) : 0;
     }();
     if (align) {
       int g = pair ? grid / 2 : grid;
@@ -424,7 +423,7 @@ bool gemm_gn_fuse_supported(const GemmDesc& d) {
   if (d.conv != CONV_3x3 && d.conv != CONV_1x1) return false;
   // 32 groups of 4, 8 or 16 channels: whole channel quads per group, groups inside one warp's 32 features
   if (d.epi != EPI_F16 || (d.N != 128 && d.N != 256 && d.N != 512) || d.b_batch > 1 || d.block_n == 32) return false;
-  if (d.e.resid != nullptr || d.e.addtab != nullptr || d.e.up2 || d.e.act != ACT_NONE) return false;
+  if (d.e.addtab != nullptr || d.e.up2 || d.e.act != ACT_NONE) return false;  // (a residual needs the dual form)
   if (d.H < 2 || d.W > SW_ROWS || SW_ROWS % d.W != 0) return false;
   const long long HW = (long long)d.H * d.W;
   if (HW % SW_ROWS != 0) return false;

@@ -63,6 +63,8 @@ struct EpiParams {
   // gn_beta: the norm's affine [N]; gn_err: set to 1 if a wait gives up (never in a healthy run)
   unsigned long long* gn_sums;
   float gn_inv_count;
+  // "dual" form: `out` receives the RAW tensor as usual (residual allowed) and gn_out2 (same layout) the normalised copy
+  __half* gn_out2;
   const float* gn_gamma;
   const float* gn_beta;
   float gn_eps;
@@ -642,7 +644,8 @@ constexpr size_t SW_SMEM_BYTES = 1024 + SW_STAGES * (SW_W_BYTES + SW_X_BYTES) + 
 // rhalf*128.. = 128 of the tile's 256 rows, walked in rounds of 32 rows.
 template <int EPI>
 __device__ __forceinline__ void sw_epilogue_tile(const GemmParams& p, uint32_t tmem_acc, int m_tile, int n_tile,
-                                                 int par, int quad, int rhalf, int lane) {
+                                                 int par, int quad, int rhalf, int lane,
+                                                 float2* stats = nullptr) {  // stats: this thread's (sum, sum of squares)
   const uint32_t taddr = tmem_acc + (static_cast<uint32_t>(quad * 32) << 16) + rhalf * 128;
   const int n = n_tile * SW_FEATS + quad * 32 + lane;  // this thread's output feature
   float gs = 0.f, gq = 0.f;  // GroupNorm sum / sum of squares of feature n over this warp's 128 rows
@@ -703,7 +706,9 @@ __device__ __forceinline__ void sw_epilogue_tile(const GemmParams& p, uint32_t t
   }
   if constexpr (EPI == EPI_F16) {
     const int rbase = m_tile * SW_ROWS + rhalf * 128;
-    if (p.epi.gn_part != nullptr && rbase < p.M) {
+    if (stats != nullptr) {
+      *stats = make_float2(gs, gq);  // the caller publishes them (gn_dual_loop)
+    } else if (p.epi.gn_part != nullptr && rbase < p.M) {
       // GroupNorm partials per (128 rows x 4 channels), no atomics (deterministic): lanes 4k..4k+3 hold one quad;
       // gn_finalize_kernel folds quads into groups and sums an image's slots in a fixed order
       gs += __shfl_xor_sync(0xffffffffu, gs, 1);
@@ -745,6 +750,29 @@ __device__ __forceinline__ void gn_store_cols(const uint32_t (&r)[32], __half* o
   }
 }
 
+// Publish a warp's per-feature (sum, sum of squares) over its 128 rows to the image's per-group accumulators.
+// Each (image, group) owns two 64-bit words: bits 63..8 accumulate the sum (sum of squares) as a 36.20 FIXED-POINT
+// integer, bits 7..0 count the contributions.  One atomic add delivers a warp's partial AND its arrival, so no fence
+// has to order data before a flag (a release cost ~3 K cycles per tile here), and integer addition is associative:
+// the totals -- and the whole decode -- are bit-identical whatever order the CTAs arrive in.
+__device__ __forceinline__ void gn_publish(const GemmParams& p, int m_tile, int n_tile, int quad, int lane, float gs,
+                                           float gq) {
+  const EpiParams& e = p.epi;
+  const int n = n_tile * SW_FEATS + quad * 32 + lane;
+  // sums over this warp's channels of each GroupNorm group (4, 8 or 16 consecutive lanes)
+  const int cpg = p.N >> 5;  // channels per group (32 groups)
+  for (int o = 1; o < cpg; o <<= 1) {
+    gs += __shfl_xor_sync(0xffffffffu, gs, o);
+    gq += __shfl_xor_sync(0xffffffffu, gq, o);
+  }
+  const int img = m_tile / p.tiles_per_img;
+  unsigned long long* gsum = e.gn_sums + ((long long)img * 32 + n / cpg) * 2;
+  if ((lane & (cpg - 1)) == 0) {
+    atomicAdd(gsum, ((unsigned long long)__double2ll_rn((double)gs * 1048576.0) << 8) + 1ull);
+    atomicAdd(gsum + 1, ((unsigned long long)__double2ll_rn((double)gq * 1048576.0) << 8) + 1ull);
+  }
+}
+
 // first pass: statistics of this warp's 32 features x 128 rows, published to the image's accumulators
 __device__ __forceinline__ void gn_pass1(const GemmParams& p, uint32_t tmem_acc, int m_tile, int n_tile, int quad,
                                          int rhalf, int lane, unsigned long long* tr) {  // tr: trace slots 4, 6
@@ -766,23 +794,21 @@ __device__ __forceinline__ void gn_pass1(const GemmParams& p, uint32_t tmem_acc,
       gq = fmaf(x, x, gq);
     }
   }
-  // sums over this warp's channels of each GroupNorm group (4, 8 or 16 consecutive lanes)
-  const int cpg = p.N >> 5;  // channels per group (32 groups)
-  for (int o = 1; o < cpg; o <<= 1) {
-    gs += __shfl_xor_sync(0xffffffffu, gs, o);
-    gq += __shfl_xor_sync(0xffffffffu, gq, o);
-  }
-  // Each (image, group) owns two 64-bit words: bits 63..8 accumulate the sum (sum of squares) as a 36.20 FIXED-POINT
-  // integer, bits 7..0 count the contributions.  One atomic add delivers a warp's partial AND its arrival, so no fence
-  // has to order data before a flag (a release cost ~3 K cycles per tile here), and integer addition is associative:
-  // the totals -- and the whole decode -- are bit-identical whatever order the CTAs arrive in.
-  const int img = m_tile / p.tiles_per_img;
-  unsigned long long* gsum = e.gn_sums + ((long long)img * 32 + n / cpg) * 2;
-  if ((lane & (cpg - 1)) == 0) {
-    atomicAdd(gsum, ((unsigned long long)__double2ll_rn((double)gs * 1048576.0) << 8) + 1ull);
-    atomicAdd(gsum + 1, ((unsigned long long)__double2ll_rn((double)gq * 1048576.0) << 8) + 1ull);
-  }
+  gn_publish(p, m_tile, n_tile, quad, lane, gs, gq);
   if (tr && lane == 0) tr[6] = clock64();  // statistics published
+}
+
+// a group's complete totals -> the affine y = a x + b of one of its channels
+__device__ __forceinline__ void gn_affine(const EpiParams& e, unsigned long long w0, unsigned long long w1, float gamma,
+                                          float beta, float& a, float& b) {
+  const double s = (double)((long long)w0 >> 8) * (1.0 / 1048576.0);
+  const double q = (double)((long long)w1 >> 8) * (1.0 / 1048576.0);
+  const double inv = (double)e.gn_inv_count;  // 1 / (pixels x channels per group)
+  const double mean = s * inv;
+  const double var = q * inv - mean * mean;
+  const float rstd = rsqrtf(fmaxf((float)var, 0.f) + e.gn_eps);
+  a = rstd * gamma;
+  b = beta - (float)mean * a;
 }
 
 // whether the image's other row tiles have contributed to this lane's group (a word is complete when its count reaches
@@ -812,16 +838,7 @@ __device__ __forceinline__ void gn_pass2(const GemmParams& p, uint32_t tmem_acc,
   const int rbase = m_tile * SW_ROWS + rhalf * 128;
   if (tr && lane == 0) tr[7] = clock64();  // the image's statistics are complete
   float a, b;
-  {
-    const double s = (double)((long long)w0 >> 8) * (1.0 / 1048576.0);
-    const double q = (double)((long long)w1 >> 8) * (1.0 / 1048576.0);
-    const double inv = (double)e.gn_inv_count;  // 1 / (pixels x channels per group)
-    const double mean = s * inv;
-    const double var = q * inv - mean * mean;
-    const float rstd = rsqrtf(fmaxf((float)var, 0.f) + e.gn_eps);
-    a = rstd * gamma;
-    b = beta - (float)mean * a;
-  }
+  gn_affine(e, w0, w1, gamma, beta, a, b);
   __half* op = static_cast<__half*>(e.out) + (long long)rbase * e.ldo + n;
   const bool sw = e.gn_swish != 0;
 #pragma unroll 1
@@ -895,6 +912,80 @@ __device__ __forceinline__ void gn_epilogue_loop(const GemmParams& p, uint32_t t
     n_tile = n_next;
     ++k;
   }
+}
+
+// ---- "dual" form: the RAW output is needed too (a ResnetBlock's output feeds the next block's shortcut as well as its
+// norm1, model.py:117-137), so the tile is stored by the ordinary epilogue (residual, fp16 rounding, statistics of the
+// fp32 values), its accumulator is released at once, and the normalised copy is written one tile LATER: by then the
+// image's other tiles have contributed (no idle wait), and the warp re-reads its own 32 features x 128 rows -- still
+// in L2 -- normalises them and stores them to gn_out2.  Compared with the separate pass this saves the DRAM read of
+// the raw tensor and a launch, and never holds tensor memory.
+template <int LDO>
+__device__ __forceinline__ void gn_dual_cols(const __half* ip, __half* op, int ldo_dyn, float a, float b, bool swish) {
+  const int ldo = LDO > 0 ? LDO : ldo_dyn;
+  __half v[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) v[j] = __ldcg(ip + j * ldo);
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    float y = fmaf(a, __half2float(v[j]), b);
+    if (swish) y = silu_f(y);
+    op[j * ldo] = __float2half_rn(y);
+  }
+}
+
+__device__ __forceinline__ void gn_dual_pass2(const GemmParams& p, int m_tile, int n_tile, int quad, int rhalf, int lane) {
+  const EpiParams& e = p.epi;
+  const int n = n_tile * SW_FEATS + quad * 32 + lane;
+  const float gamma = __ldg(e.gn_gamma + n), beta = __ldg(e.gn_beta + n);
+  unsigned long long w0, w1;
+  const long long t0 = clock64();
+  while (!gn_ready(p, m_tile, n_tile, quad, lane, w0, w1)) {
+    if (clock64() - t0 > (1LL << 31)) {  // ~1 s: give up instead of hanging the device
+      *e.gn_err = 1;
+      break;
+    }
+  }
+  float a, b;
+  gn_affine(e, w0, w1, gamma, beta, a, b);
+  const long long off = (long long)(m_tile * SW_ROWS + rhalf * 128) * e.ldo + n;
+  const __half* ip = static_cast<const __half*>(e.out) + off;
+  __half* op = e.gn_out2 + off;
+  const bool sw = e.gn_swish != 0;
+#pragma unroll 1
+  for (int c = 0; c < 128; c += 32) {
+    const long long o = (long long)c * e.ldo;
+    switch (e.ldo) {
+      case 128: gn_dual_cols<128>(ip + o, op + o, e.ldo, a, b, sw); break;
+      case 256: gn_dual_cols<256>(ip + o, op + o, e.ldo, a, b, sw); break;
+      case 512: gn_dual_cols<512>(ip + o, op + o, e.ldo, a, b, sw); break;
+      default: gn_dual_cols<0>(ip + o, op + o, e.ldo, a, b, sw); break;
+    }
+  }
+}
+
+template <class Coords, class Release>
+__device__ __forceinline__ void gn_dual_loop(const GemmParams& p, uint32_t tmem_base, uint64_t* tmem_full, int first,
+                                             int stride, int total, int quad, int rhalf, int lane, Coords coords,
+                                             Release release) {
+  int pm = -1, pn = 0;  // the tile whose normalised copy is still owed
+  int k = 0;
+  for (int t = first; t < total; t += stride, ++k) {
+    int m_tile, n_tile;
+    coords(t, m_tile, n_tile);
+    mbar_wait(&tmem_full[k & 1], (k >> 1) & 1);
+    tc_fence_after();
+    float2 st = make_float2(0.f, 0.f);
+    sw_epilogue_tile<EPI_F16>(p, tmem_base + (k & 1) * SW_ROWS, m_tile, n_tile, 0, quad, rhalf, lane, &st);
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) release(k & 1);
+    gn_publish(p, m_tile, n_tile, quad, lane, st.x, st.y);
+    if (pm >= 0) gn_dual_pass2(p, pm, pn, quad, rhalf, lane);
+    pm = m_tile;
+    pn = n_tile;
+  }
+  if (pm >= 0) gn_dual_pass2(p, pm, pn, quad, rhalf, lane);
 }
 
 template <int EPI>
@@ -1014,7 +1105,15 @@ gemm_sw_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
     const int rhalf = ew >> 2;   // which 128 of the tile's 256 rows
     int acc = 0;
     uint32_t acc_phase = 0;
-    if (EPI == EPI_F16 && p.epi.gn_sums != nullptr) {  // (num_par == 1 in this mode)
+    if (EPI == EPI_F16 && p.epi.gn_sums != nullptr && p.epi.gn_out2 != nullptr) {
+      gn_dual_loop(
+          p, tmem_base, tmem_full, blockIdx.x, gridDim.x, total_tiles, quad, rhalf, lane,
+          [&](int t, int& m_tile, int& n_tile) {
+            m_tile = t / p.num_n_tiles;
+            n_tile = t - m_tile * p.num_n_tiles;
+          },
+          [&](int a) { mbar_arrive(&tmem_empty[a]); });
+    } else if (EPI == EPI_F16 && p.epi.gn_sums != nullptr) {  // (num_par == 1 in this mode)
       gn_epilogue_loop(
           p, tmem_base, tmem_full, blockIdx.x, gridDim.x, total_tiles, quad, rhalf, lane, blockIdx.x == 0 && warp == 2,
           [&](int t, int& m_tile, int& n_tile) {
@@ -1217,7 +1316,19 @@ gemm_sw2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
     const int rhalf = ew >> 2;
     int acc = 0;
     uint32_t acc_phase = 0;
-    if (EPI == EPI_F16 && p.epi.gn_sums != nullptr) {  // (num_par == 1, an even number of feature tiles in this mode)
+    if (EPI == EPI_F16 && p.epi.gn_sums != nullptr && p.epi.gn_out2 != nullptr) {
+      gn_dual_loop(
+          p, tmem_base, tmem_full, pair_id, num_pairs, total_tiles, quad, rhalf, lane,
+          [&](int t, int& m_tile, int& n_tile) {
+            int n_pair;
+            sw2_tile_coords(t, p.num_m_tiles, pairs_n, p.band_n, m_tile, n_pair);
+            n_tile = 2 * n_pair + (int)rank;
+          },
+          [&](int a) {
+            if (rank == 0) mbar_arrive(&tmem_empty[a]);
+            else mbar_arrive_remote(&tmem_empty[a], 0);
+          });
+    } else if (EPI == EPI_F16 && p.epi.gn_sums != nullptr) {  // (num_par == 1, an even number of feature tiles in this mode)
       gn_epilogue_loop(
           p, tmem_base, tmem_full, pair_id, num_pairs, total_tiles, quad, rhalf, lane, blockIdx.x == 0 && warp == 2,
           [&](int t, int& m_tile, int& n_tile) {

@@ -277,21 +277,26 @@ GemmDesc conv_desc(const Ctx& c, const Conv& cv, const __half* x, int H, const _
   return d;
 }
 
+// `norm_copy` with `out_norm` ("dual" form): `out` receives the raw tensor (+ residual) as usual and `norm_copy` its
+// normalised copy, written by the same launch one tile later from the warp's own L2-resident rows.
 int run_conv(Ctx& c, const Conv& cv, const __half* x, int H, const __half* resid, __half* out, const Norm* next,
-             bool fuse_input_norm = false, const Norm* out_norm = nullptr) {
+             bool fuse_input_norm = false, const Norm* out_norm = nullptr, __half* norm_copy = nullptr,
+             bool norm_swish = true) {
   GemmDesc d = conv_desc(c, cv, x, H, resid, out);
   if (next != nullptr) {
     if (next->c != cv.cout || cv.cout % 128 != 0) return set_error("rgm_vae: GroupNorm partials need a 128-multiple channel count");
     d.e.gn_part = static_cast<float*>(c.L->gnpart.p);
   }
   if (out_norm != nullptr) {
-    if (next != nullptr || out_norm->c != cv.cout) return set_error("rgm_vae: bad GroupNorm-in-epilogue request");
+    if (next != nullptr || out_norm->c != cv.cout || (resid != nullptr && norm_copy == nullptr))
+      return set_error("rgm_vae: bad GroupNorm-in-epilogue request");
     d.e.gn_sums = static_cast<unsigned long long*>(c.L->gncount.p);
     d.e.gn_gamma = out_norm->gamma;
     d.e.gn_beta = out_norm->beta;
     d.e.gn_eps = 1e-6f;
-    d.e.gn_swish = 1;
+    d.e.gn_swish = norm_swish ? 1 : 0;
     d.e.gn_err = c.m->gn_err;
+    d.e.gn_out2 = norm_copy;
     RGM_CUDA_OK(cudaMemsetAsync(c.L->gncount.p, 0, gn_scratch_bytes(c.nt), c.st));
   }
   if (fuse_input_norm) {  // x is RAW: normalise + swish with the current affine inside the operand path (conv_gn.cuh)
@@ -334,52 +339,99 @@ bool can_fuse_out_norm(const Ctx& c, const Conv& cv, int H) {
   return gemm_gn_fuse_supported(conv_desc(c, cv, nullptr, H, nullptr, nullptr));
 }
 
-// ResnetBlock (model.py:117-137). x: input [nt,H,H,cin] whose GroupNorm affine (norm1) is current in L->abbuf -- its
-// producer's epilogue put it there -- unless stats_from_tensor; t, h: scratch; out may alias neither x nor h.  `next` =
-// the norm that consumes this block's output (its affine is left current), or null.
-int run_res(Ctx& c, const Res& r, const __half* x, int H, __half* t, __half* h, __half* out, const Norm* next,
-            bool stats_from_tensor = false) {
-  const int HW = H * H;
-  if (stats_from_tensor)  // x did not come out of a GEMM epilogue (the stems): one direct statistics pass
-    RGM_CUDA_OK(launch_gn_stats(x, r.n1.gamma, r.n1.beta, c.ab(), c.nt, HW, r.n1.c, 1e-6f, c.st));
-  const bool e1 = can_fuse_out_norm(c, r.c1, H);  // conv1 writes swish(norm2(conv1(.))) itself: no pass over h
-  const bool f1 = can_fuse_norm(c, r.c1, H), f2 = !e1 && can_fuse_norm(c, r.c2, H);
-  if (f1) {
-    if (run_conv(c, r.c1, x, H, nullptr, h, e1 ? nullptr : &r.n2, true, e1 ? &r.n2 : nullptr)) return -1;
-  } else {
-    RGM_CUDA_OK(launch_gn_apply(x, c.ab(), t, c.nt, HW, r.n1.c, 1, c.st));
-    if (run_conv(c, r.c1, t, H, nullptr, h, e1 ? nullptr : &r.n2, false, e1 ? &r.n2 : nullptr)) return -1;
-  }
-  if (!f2 && !e1) RGM_CUDA_OK(launch_gn_apply(h, c.ab(), t, c.nt, HW, r.n2.c, 1, c.st));
-  const __half* resid = x;
-  if (r.has_nin) {
-    if (run_conv(c, r.nin, x, H, nullptr, out, nullptr)) return -1;
-    resid = out;  // conv2 adds the shortcut it finds in `out` and overwrites it (same thread reads then writes)
-  }
-  return run_conv(c, r.c2, (f2 || e1) ? h : t, H, resid, out, next, f2);
+// Which of the lane's four activation buffers holds the current tensor x and -- when its producer already wrote the
+// normalised copy the next GroupNorm would compute ("dual" epilogue) -- that copy (else -1).
+struct Act {
+  int x = 0;
+  int xn = -1;
+};
+
+int take_free(bool (&used)[4]) {
+  for (int i = 0; i < 4; ++i)
+    if (!used[i]) {
+      used[i] = true;
+      return i;
+    }
+  return -1;  // cannot happen: at most three buffers are live at any point of a block
 }
 
-// AttnBlock (model.py:168-192) at 16x16: single head over the 256 positions of a tile.  x = buf[cur] (its GroupNorm
-// partials current); the result x + proj_out(attention) lands in buf[0] with its partials current.  cur must be 3.
+// ResnetBlock (model.py:117-137) on buf[a.x] (its norm1 affine current in L->abbuf -- its producer's epilogue put it
+// there -- unless stats_from_tensor, or already applied: buf[a.xn]).  On return a.x is the block's output and a.xn its
+// copy normalised by `next` (with swish iff next_swish) when want_copy and the layer qualifies; otherwise the affine of
+// `next` is left current.  next == nullptr: nobody normalises the output (an upsample / downsample conv follows).
+int run_res(Ctx& c, const Res& r, __half* const* buf, Act& a, int H, const Norm* next, bool next_swish = true,
+            bool want_copy = true, bool stats_from_tensor = false) {
+  const int HW = H * H;
+  bool used[4] = {false, false, false, false};
+  used[a.x] = true;
+  if (a.xn >= 0) used[a.xn] = true;
+  const __half* x = buf[a.x];
+  if (stats_from_tensor && a.xn < 0)  // x did not come out of a GEMM epilogue (the stems): one direct statistics pass
+    RGM_CUDA_OK(launch_gn_stats(x, r.n1.gamma, r.n1.beta, c.ab(), c.nt, HW, r.n1.c, 1e-6f, c.st));
+  const bool e1 = can_fuse_out_norm(c, r.c1, H);  // conv1 writes swish(norm2(conv1(.))) itself: no pass over h
+  const bool f1 = a.xn < 0 && can_fuse_norm(c, r.c1, H), f2 = !e1 && can_fuse_norm(c, r.c2, H);
+  int in1 = a.x;  // (f1: the raw tensor, normalised inside the operand path)
+  if (a.xn >= 0) {
+    in1 = a.xn;
+  } else if (!f1) {
+    in1 = take_free(used);
+    RGM_CUDA_OK(launch_gn_apply(x, c.ab(), buf[in1], c.nt, HW, r.n1.c, 1, c.st));
+  }
+  const int h = take_free(used);
+  if (run_conv(c, r.c1, buf[in1], H, nullptr, buf[h], e1 ? nullptr : &r.n2, f1, e1 ? &r.n2 : nullptr)) return -1;
+  if (in1 != a.x) used[in1] = false;  // the normalised input is dead
+  int in2 = h;
+  if (!e1 && !f2) {
+    in2 = take_free(used);
+    RGM_CUDA_OK(launch_gn_apply(buf[h], c.ab(), buf[in2], c.nt, HW, r.n2.c, 1, c.st));
+    used[h] = false;
+  }
+  const int o = take_free(used);
+  const __half* resid = x;
+  if (r.has_nin) {
+    if (run_conv(c, r.nin, x, H, nullptr, buf[o], nullptr)) return -1;
+    resid = buf[o];  // conv2 adds the shortcut it finds in `out` and overwrites it (same thread reads then writes)
+  }
+  const bool dual = next != nullptr && want_copy && can_fuse_out_norm(c, r.c2, H);
+  const int on = dual ? take_free(used) : -1;  // x, conv2's input and the output are live: the fourth buffer is free
+  if (run_conv(c, r.c2, buf[in2], H, resid, buf[o], dual ? nullptr : next, f2, dual ? next : nullptr,
+               dual ? buf[on] : nullptr, next_swish))
+    return -1;
+  a.x = o;
+  a.xn = on;
+  return 0;
+}
+
+// AttnBlock (model.py:168-192) at 16x16: single head over the 256 positions of a tile, on buf[a.x] (the affine of `norm`
+// current, or already applied -- without swish -- in buf[a.xn]).  On return a.x = x + proj_out(attention) and a.xn its
+// copy normalised by `next` (or -1 with the affine of `next` current).  Uses all four buffers.
 int run_mid_attn(Ctx& c, const Norm& norm, const Conv& cq, const Conv& ck, const Conv& cvv, const Conv& cproj,
-                 __half* const* buf, int cur, int H, int C, const Norm* next) {
+                 __half* const* buf, Act& a, int H, int C, const Norm* next) {
   const int nt = c.nt;
   cudaStream_t st = c.st;
   Vae::Lane* L = c.L;
-  float2* ab = c.ab();
   const int HW = H * H;
-  __half* x = buf[cur];
-  __half* hn = buf[0];
+  bool used[4] = {false, false, false, false};
+  used[a.x] = true;
+  if (a.xn >= 0) used[a.xn] = true;
+  __half* x = buf[a.x];
   if (norm.c != C) return set_error("rgm_vae: attention norm width");
-  RGM_CUDA_OK(launch_gn_apply(x, ab, hn, nt, HW, C, 0, st));  // the affine of `norm` is current (producer's epilogue)
-  // q, k, v, v^T, P carve buf[1] and buf[2] (each holds >= 4 tensors of this size: buffers are sized for 128x128x256)
+  int ihn = a.xn;
+  if (ihn < 0) {
+    ihn = take_free(used);
+    RGM_CUDA_OK(launch_gn_apply(x, c.ab(), buf[ihn], nt, HW, C, 0, st));  // the affine of `norm` is current
+  }
+  __half* hn = buf[ihn];
+  const int b1 = take_free(used), b2 = take_free(used);
+  // q, k, v and v^T, P, attention output carve two buffers (each holds >= 4 tensors of this size: buffers are sized for
+  // 128x128x256)
   const long long tsz = (long long)nt * HW * C;
-  __half* q = buf[1];
-  __half* k = buf[1] + tsz;
-  __half* v = buf[1] + 2 * tsz;
-  __half* vT = buf[2];
-  __half* P = buf[2] + tsz;
-  __half* ao = buf[2] + 2 * tsz;
+  __half* q = buf[b1];
+  __half* k = buf[b1] + tsz;
+  __half* v = buf[b1] + 2 * tsz;
+  __half* vT = buf[b2];
+  __half* P = buf[b2] + tsz;
+  __half* ao = buf[b2] + 2 * tsz;
   if (run_conv(c, cq, hn, H, nullptr, q, nullptr)) return -1;
   if (run_conv(c, ck, hn, H, nullptr, k, nullptr)) return -1;
   if (run_conv(c, cvv, hn, H, nullptr, v, nullptr)) return -1;
@@ -424,7 +476,13 @@ int run_mid_attn(Ctx& c, const Norm& norm, const Conv& cq, const Conv& ck, const
     d.e.alpha = 1.f;
     RGM_VGEMM_OK(d);
   }
-  return run_conv(c, cproj, ao, H, x, hn, next);  // x + proj_out(attention)
+  // x + proj_out(attention) over the (dead) normalised input; q / k / v are dead too: their buffer takes the copy
+  const bool dual = next != nullptr && can_fuse_out_norm(c, cproj, H);
+  if (run_conv(c, cproj, ao, H, x, hn, dual ? nullptr : next, false, dual ? next : nullptr, dual ? buf[b1] : nullptr, true))
+    return -1;
+  a.x = ihn;
+  a.xn = dual ? b1 : -1;
+  return 0;
 }
 
 int decode_chunk(Vae* m, Vae::Lane* L, const float* lat, float scale, float* roll, int n_cand, int Hlat, int roll_ch,
@@ -438,33 +496,29 @@ int decode_chunk(Vae* m, Vae::Lane* L, const float* lat, float scale, float* rol
   RGM_CUDA_OK(launch_vae_stem(lat, scale, m->pq_w, m->pq_b, m->cin_w, m->cin_b, buf[0], n_cand, Hlat, tile0, nt, C,
                               st));
   // mid.block_1: the stem has no GEMM epilogue, so its GroupNorm statistics come from a direct pass
-  if (run_res(c, m->mid1, buf[0], H, buf[1], buf[2], buf[3], &m->attn_norm, /*stats_from_tensor=*/true)) return -1;
-  int cur = 3;  // buf[cur] holds x
+  Act a;  // the stem wrote buf[0]
+  if (run_res(c, m->mid1, buf, a, H, &m->attn_norm, /*next_swish=*/false, true, /*stats_from_tensor=*/true)) return -1;
   // mid.attn_1 (model.py:168-192)
-  if (run_mid_attn(c, m->attn_norm, m->attn_q, m->attn_k, m->attn_v, m->attn_proj, buf, cur, H, C, &m->mid2.n1)) return -1;
-  cur = 0;
+  if (run_mid_attn(c, m->attn_norm, m->attn_q, m->attn_k, m->attn_v, m->attn_proj, buf, a, H, C, &m->mid2.n1)) return -1;
   // mid.block_2
-  {
-    const int o = (cur + 3) & 3;
-    if (run_res(c, m->mid2, buf[cur], H, buf[(cur + 1) & 3], buf[(cur + 2) & 3], buf[o], &m->up[m->n_levels - 1][0].n1))
-      return -1;
-    cur = o;
-  }
+  if (run_res(c, m->mid2, buf, a, H, &m->up[m->n_levels - 1][0].n1)) return -1;
   for (int lvl = m->n_levels - 1; lvl >= 0; --lvl) {
     for (int b = 0; b <= m->nres; ++b) {
-      const int o = (cur + 3) & 3;
-      // who normalises this block's output: the next block, norm_out after the last one, nobody before an upsample conv
+      // who normalises this block's output: the next block, norm_out after the last one (inside vae_out_kernel, from the
+      // raw tensor and the affine: no copy), nobody before an upsample conv
+      const bool last = b == m->nres && lvl == 0;
       const Norm* next = b < m->nres ? &m->up[lvl][b + 1].n1 : (lvl == 0 ? &m->norm_out : nullptr);
-      if (run_res(c, m->up[lvl][b], buf[cur], H, buf[(cur + 1) & 3], buf[(cur + 2) & 3], buf[o], next)) return -1;
-      cur = o;
+      if (run_res(c, m->up[lvl][b], buf, a, H, next, true, /*want_copy=*/!last)) return -1;
     }
     if (lvl != 0) {
-      const int o = (cur + 1) & 3;
-      if (run_conv(c, m->upsample[lvl], buf[cur], H, nullptr, buf[o], &m->up[lvl - 1][0].n1)) return -1;
-      cur = o;
+      const int o = (a.x + 1) & 3;  // (a.xn is -1 here)
+      if (run_conv(c, m->upsample[lvl], buf[a.x], H, nullptr, buf[o], &m->up[lvl - 1][0].n1)) return -1;
+      a.x = o;
+      a.xn = -1;
       H *= 2;
     }
   }
+  const int cur = a.x;
   // norm_out + swish + conv_out, assembled into the roll: one fused CUDA-core kernel (aux_kernels.cu)
   {
     if (H != 128) return set_error("rgm_vae: decoder output is not 128x128 (the roll kernels assume 128x128 tiles)");
@@ -483,50 +537,32 @@ int encode_chunk(Vae* m, Vae::Lane* L, const float* x, float* moments, int t0, i
   int H = 128;
   RGM_CUDA_OK(launch_vae_enc_stem(x + (long long)t0 * m->in_ch * 128 * 128, m->e_cin_w, m->e_cin_b, buf[0], nt, m->in_ch,
                                   m->ch, st));
-  int cur = 0;
+  Act a;  // the stem wrote buf[0]
   bool first = true;
   for (int lvl = 0; lvl < m->n_levels; ++lvl) {
     const bool last_lvl = lvl == m->n_levels - 1;
     for (int b = 0; b < m->nres; ++b) {
-      const int o = (cur + 3) & 3;
       // who normalises this block's output: the next block, mid.block_1 after the last level, nobody before a Downsample
       const Norm* next = b < m->nres - 1 ? &m->down[lvl][b + 1].n1 : (last_lvl ? &m->e_mid1.n1 : nullptr);
-      if (run_res(c, m->down[lvl][b], buf[cur], H, buf[(cur + 1) & 3], buf[(cur + 2) & 3], buf[o], next, first)) return -1;
-      cur = o;
+      if (run_res(c, m->down[lvl][b], buf, a, H, next, true, true, first)) return -1;
       first = false;
     }
     if (!last_lvl) {
-      const int o = (cur + 1) & 3;
-      if (run_conv(c, m->downsample[lvl], buf[cur], H, nullptr, buf[o], &m->down[lvl + 1][0].n1)) return -1;  // H -> H/2
-      cur = o;
+      const int o = (a.x + 1) & 3;  // (a.xn is -1 here)
+      if (run_conv(c, m->downsample[lvl], buf[a.x], H, nullptr, buf[o], &m->down[lvl + 1][0].n1)) return -1;  // H -> H/2
+      a.x = o;
+      a.xn = -1;
       H /= 2;
     }
   }
   if (H != 16) return set_error("rgm_vae_encode: encoder output is not 16x16");
   const int C = m->e_mid1.c1.cin;
-  {
-    const int o = 3;  // run_mid_attn wants its input in buf[3]
-    if (cur == o) {   // (with 4 levels x 2 blocks + 3 downsamples cur is 3 here only by accident of the ping-pong)
-      const int o2 = (cur + 3) & 3;
-      if (run_res(c, m->e_mid1, buf[cur], H, buf[(cur + 1) & 3], buf[(cur + 2) & 3], buf[o2], &m->e_attn_norm)) return -1;
-      RGM_CUDA_OK(cudaMemcpyAsync(buf[o], buf[o2], (size_t)nt * H * H * C * sizeof(__half), cudaMemcpyDeviceToDevice, st));
-    } else {
-      int t1 = -1, t2 = -1;  // two scratch buffers that are neither cur nor 3
-      for (int i = 0; i < 3; ++i)
-        if (i != cur) (t1 < 0 ? t1 : t2) = i;
-      if (run_res(c, m->e_mid1, buf[cur], H, buf[t1], buf[t2], buf[o], &m->e_attn_norm)) return -1;
-    }
-    cur = o;
-  }
-  if (run_mid_attn(c, m->e_attn_norm, m->e_attn_q, m->e_attn_k, m->e_attn_v, m->e_attn_proj, buf, cur, H, C,
-                   &m->e_mid2.n1))
+  if (run_res(c, m->e_mid1, buf, a, H, &m->e_attn_norm, /*next_swish=*/false)) return -1;
+  if (run_mid_attn(c, m->e_attn_norm, m->e_attn_q, m->e_attn_k, m->e_attn_v, m->e_attn_proj, buf, a, H, C, &m->e_mid2.n1))
     return -1;
-  cur = 0;
-  {
-    const int o = (cur + 3) & 3;
-    if (run_res(c, m->e_mid2, buf[cur], H, buf[(cur + 1) & 3], buf[(cur + 2) & 3], buf[o], &m->e_norm_out)) return -1;
-    cur = o;
-  }
+  // norm_out is applied by the pass below, from the raw tensor and the affine: no normalised copy
+  if (run_res(c, m->e_mid2, buf, a, H, &m->e_norm_out, true, /*want_copy=*/false)) return -1;
+  const int cur = a.x;
   // norm_out + swish, conv_out (C -> 2*zc, fp32 out, feature dim padded to 32), quant_conv 1x1 -> NCHW moments
   __half* t = buf[(cur + 1) & 3];
   RGM_CUDA_OK(launch_gn_apply(buf[cur], c.ab(), t, nt, H * H, C, 1, st));

@@ -180,7 +180,8 @@ def test_conv_with_groupnorm_of_its_own_output(cuda, n, H, cin, cout, kind, swis
     out = torch.empty(n, H, H, cout, device=cuda, dtype=torch.float16)
     for _ in range(2):  # twice: accumulators and counters are re-armed by every call
         _lib.call("rgm_conv_norm_f16", _lib.ptr(x), _lib.ptr(wp), _lib.ptr(bias), _lib.ptr(gamma), _lib.ptr(beta),
-                  _lib.ptr(out), n, H, H, cin, cout, kind, swish, _lib.ptr(scratch), _lib.ptr(err), _lib.stream_ptr())
+                  None, None, _lib.ptr(out), n, H, H, cin, cout, kind, swish, _lib.ptr(scratch), _lib.ptr(err),
+                  _lib.stream_ptr())
     torch.cuda.synchronize()
     assert err.item() == 0, "a GroupNorm-in-epilogue wait gave up"
     count = scratch.view(n, 64, 2)[:, :, 0] & 255   # low byte of every accumulator word = contributions received
@@ -207,3 +208,62 @@ def test_conv_with_groupnorm_of_its_own_output(cuda, n, H, cin, cout, kind, swis
     torch.cuda.synchronize()
     d = (out.float() - two.float()).abs().max().item()
     assert d <= 4e-3 * two.float().abs().max().item() + 1e-3, d
+
+
+@pytest.mark.parametrize("n,H,cin,cout,resid", [
+    (3, 32, 128, 128, "separate"),
+    (130, 128, 128, 128, "separate"),  # a full bench chunk of the 128x128 level
+    (10, 64, 256, 256, "in_place"),    # CTA pairs; the shortcut is found in the output buffer (nin_shortcut case)
+    (40, 16, 512, 512, None),
+])
+def test_conv_dual_raw_and_normalised_output(cuda, n, H, cin, cout, resid):
+    """conv2 of a ResnetBlock: raw = conv(x) + shortcut AND swish(GroupNorm(raw)) from one launch (gemm_tc.cuh
+    gn_dual_loop).  The raw tensor must equal the plain convolution's bit for bit; the normalised copy is compared with
+    the library's own normalise pass on that raw tensor (same fp16 inputs, statistics of the fp32 values) and torch."""
+    g = torch.Generator(device="cpu").manual_seed(n * 131 + H + cin + cout)
+    x = (torch.randn(n, H, H, cin, generator=g) * 1.2).to(cuda).half()
+    w = (torch.randn(cout, cin, 3, 3, generator=g) / (cin * 9) ** 0.5).to(cuda)
+    bias = torch.randn(cout, generator=g).to(cuda)
+    gamma = (torch.rand(cout, generator=g) + 0.5).to(cuda)
+    beta = (torch.randn(cout, generator=g) * 0.3).to(cuda)
+    res = torch.randn(n, H, H, cout, generator=g).to(cuda).half() if resid else None
+    wp = _pack(w, 1)
+    plain = torch.empty(n, H, H, cout, device=cuda, dtype=torch.float16)
+    if resid == "in_place":
+        plain.copy_(res)
+        _lib.call("rgm_conv_f16", _lib.ptr(x), _lib.ptr(wp), _lib.ptr(bias), _lib.ptr(plain), _lib.ptr(plain), n, H, H,
+                  cin, cout, 1, 0, None, _lib.stream_ptr())
+    else:
+        plain = _conv(x, wp, bias, cout, 1, resid=res)
+    scratch = torch.full((n * 128,), -1, device=cuda, dtype=torch.int32)
+    err = torch.zeros(1, device=cuda, dtype=torch.int32)
+    raw = torch.empty_like(plain)
+    out = torch.empty_like(plain)
+    rp = res
+    if resid == "in_place":
+        raw.copy_(res)
+        rp = raw
+    _lib.call("rgm_conv_norm_f16", _lib.ptr(x), _lib.ptr(wp), _lib.ptr(bias), _lib.ptr(gamma), _lib.ptr(beta),
+              _lib.ptr(rp), _lib.ptr(raw), _lib.ptr(out), n, H, H, cin, cout, 1, 1, _lib.ptr(scratch), _lib.ptr(err),
+              _lib.stream_ptr())
+    torch.cuda.synchronize()
+    assert err.item() == 0, "a GroupNorm-in-epilogue wait gave up"
+    assert torch.equal(raw, plain)
+    conv = F.conv2d(x.float().permute(0, 3, 1, 2), w.half().float(), bias, padding=1)
+    if res is not None:
+        conv = conv + res.float().permute(0, 3, 1, 2)
+    cpg = cout // 32
+    c32 = conv.permute(0, 2, 3, 1).reshape(n, H * H, 32, cpg)
+    mean = c32.mean(dim=(1, 3))
+    rstd = (c32.var(dim=(1, 3), unbiased=False) + 1e-6).rsqrt()
+    a = rstd.repeat_interleave(cpg, dim=1) * gamma
+    b = beta - mean.repeat_interleave(cpg, dim=1) * a
+    two = torch.empty_like(out)
+    ab = torch.stack((a, b), dim=-1).contiguous()
+    _lib.call("rgm_gn_apply_f16", _lib.ptr(raw), _lib.ptr(ab), _lib.ptr(two), n, H * H, cout, 1, _lib.stream_ptr())
+    torch.cuda.synchronize()
+    d = (out.float() - two.float()).abs()
+    assert d.max().item() <= 2e-3 * two.float().abs().max().item() + 1e-3, d.max().item()
+    assert (d > 0).float().mean().item() < 0.02   # same inputs, statistics equal to ~1e-6: rare last-bit differences
+    ref = F.silu(F.group_norm(conv, 32, gamma, beta, eps=1e-6)).permute(0, 2, 3, 1)
+    assert (out.float() - ref).abs().max().item() <= 3e-3 * ref.abs().max().item() + 1e-3

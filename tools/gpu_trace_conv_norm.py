@@ -14,8 +14,11 @@ for (n, H, cin, cout) in ((128, 128, 128, 128), (128, 64, 256, 256)):
     scratch = torch.zeros(n * 128, device=dev, dtype=torch.int32)
     err = torch.zeros(1, device=dev, dtype=torch.int32)
     plain = lambda: _lib.call("rgm_conv_f16", _lib.ptr(x), _lib.ptr(w), _lib.ptr(bias), None, _lib.ptr(out), n, H, H, cin, cout, 1, 0, _lib.ptr(part), _lib.stream_ptr())
-    fused = lambda: _lib.call("rgm_conv_norm_f16", _lib.ptr(x), _lib.ptr(w), _lib.ptr(bias), _lib.ptr(gamma), _lib.ptr(beta), _lib.ptr(out), n, H, H, cin, cout, 1, 1, _lib.ptr(scratch), _lib.ptr(err), _lib.stream_ptr())
-    for name, fn, dbg in (("plain", plain, 0), ("norm in epilogue", fused, 0), ("norm in epilogue, no wait", fused, 16)):
+    fused = lambda: _lib.call("rgm_conv_norm_f16", _lib.ptr(x), _lib.ptr(w), _lib.ptr(bias), _lib.ptr(gamma), _lib.ptr(beta), None, None, _lib.ptr(out), n, H, H, cin, cout, 1, 1, _lib.ptr(scratch), _lib.ptr(err), _lib.stream_ptr())
+    raw = torch.empty_like(out)
+    dual = lambda: _lib.call("rgm_conv_norm_f16", _lib.ptr(x), _lib.ptr(w), _lib.ptr(bias), _lib.ptr(gamma), _lib.ptr(beta), _lib.ptr(x) if cin == cout else None, _lib.ptr(raw), _lib.ptr(out), n, H, H, cin, cout, 1, 1, _lib.ptr(scratch), _lib.ptr(err), _lib.stream_ptr())
+    plain_res = lambda: _lib.call("rgm_conv_f16", _lib.ptr(x), _lib.ptr(w), _lib.ptr(bias), _lib.ptr(x), _lib.ptr(raw), n, H, H, cin, cout, 1, 0, _lib.ptr(part), _lib.stream_ptr())
+    for name, fn, dbg in (("plain", plain, 0), ("norm in epilogue", fused, 0), ("norm in epilogue, no wait", fused, 16), ("plain + residual", plain_res, 0), ("dual: raw + residual and normalised copy", dual, 0)):
         os.environ["RGM_GEMM_DEBUG"] = str(dbg)
         for _ in range(3): fn()
         torch.cuda.synchronize()

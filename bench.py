@@ -461,6 +461,7 @@ def run_b200(args):
     ms, ms_e2e = dist_util.max_over_ranks(ms, dev), dist_util.max_over_ranks(ms_e2e, dev)
     gathered = dist_util.gather_samples(x)  # once, outside the timed region (scripts/cfg_sample.py:102-109)
     finite = bool(torch.isfinite(gathered).all().item()) and gathered.shape[0] == world * B
+    gn_timeouts = int(vae.gn_timeouts())
     dist_util.shard_candidates(False)
 
     # ---- extra legs (see the module docstring) ----------------------------------------------------------------------
@@ -551,7 +552,12 @@ def run_b200(args):
                          "dominant_launch": dominant},
             "step_tflops_algorithmic": step_tflops,
             "finite": finite,
+            # convolutions that normalise their own output wait for each other's tiles; a wait that gave up would have
+            # produced garbage -- never in a healthy run, and checked here so that such a run cannot report a number
+            "gn_timeouts": gn_timeouts,
         }
+        if gn_timeouts:
+            raise SystemExit("bench: a GroupNorm-in-epilogue wait gave up (rgm_vae_gn_timeouts != 0): results invalid")
         if extra:
             line["extra"] = extra
         if world == 1 and not args.no_cpu_baseline and config == "c3":

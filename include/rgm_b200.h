@@ -203,7 +203,8 @@ int rgm_conv_gn_f16(const void* x16_raw, const float* ab_in, const void* w16_pac
                     void* stream);
 /* swish(GroupNorm_32(conv(x))) in ONE kernel with the normalisation applied to the convolution's OWN output
  * (reference model.py:119-124: h = conv1(..); h = norm2(h); h = nonlinearity(h)): the CTAs of an image exchange their
- * partial statistics while the accumulators wait in tensor memory, so the raw output is never written.  kind 0 / 1,
+ * partial statistics while the accumulators wait in tensor memory, so the raw output is never written.  kind 0 / 1
+ * (kind 2, the upsample conv with W a multiple of 32, in the dual form only),
  * Cout in {128, 256, 512}, H*W a multiple of 256; gamma / beta f32 [Cout]; gn_scratch: n * 512 bytes of device
  * scratch (per-group statistics accumulators that also count arrivals, zeroed by the call); gn_err: device int that is set to 1
  * if a wait gives up (never in a healthy run).  swish = 0 applies the norm only.

@@ -289,12 +289,18 @@ int rgm_conv_norm_f16(const void* x16, const void* w16_packed, const float* bias
   d.lda = Cin;
   d.B = static_cast<const __half*>(w16_packed);
   d.N = Cout;
-  d.rows_b = Cout;
+  d.rows_b = (kind == CONV_UP2 ? 4 : 1) * Cout;
   d.conv = kind;
   d.epi = EPI_F16;
   d.e.ldo = Cout;
   d.e.bias = bias;
   d.e.alpha = 1.f;
+  if (kind == CONV_UP2) {
+    if (raw16 == nullptr) return set_error("rgm_conv_norm_f16: the upsample conv needs the dual form (raw16)");
+    d.e.up2 = 1;
+    d.e.upH = H;
+    d.e.upW = W;
+  }
   if (!gemm_gn_fuse_supported(d))
     return set_error("rgm_conv_norm_f16: needs a 3x3 / 1x1 conv with 128 / 256 / 512 output features on images of a multiple "
                      "of 256 pixels that span no more tiles than there are resident CTAs");

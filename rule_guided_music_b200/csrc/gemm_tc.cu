@@ -351,8 +351,10 @@ cudaError_t launch_gemm(const GemmDesc& d, cudaStream_t stream, std::string* err
   if (gn_fuse) {
     // GroupNorm inside the epilogue (gn_epilogue_loop): whole 256-row tiles of one image, statically assigned tiles,
     // every CTA of the grid resident, an image's tiles within one grid-stride of each other
-    if (!sw || d.epi != EPI_F16 || p.num_par != 1 || down || (d.e.resid != nullptr && d.e.gn_out2 == nullptr) ||
-        (d.e.resid != nullptr && d.e.ldr != d.e.ldo) || d.e.addtab != nullptr || d.e.up2 ||
+    const bool up_ok = d.e.up2 && d.e.gn_out2 != nullptr && d.e.upW % 32 == 0 && p.par_fast && d.e.resid == nullptr;
+    if (!sw || d.epi != EPI_F16 || (p.num_par != 1 && !up_ok) || down ||
+        (d.e.resid != nullptr && d.e.gn_out2 == nullptr) || (d.e.resid != nullptr && d.e.ldr != d.e.ldo) ||
+        d.e.addtab != nullptr || (d.e.up2 && !up_ok) ||
         d.e.act != ACT_NONE || d.e.gn_sums == nullptr || d.e.gn_gamma == nullptr || d.e.gn_beta == nullptr ||
         d.e.gn_err == nullptr || d.b_batch > 1)
       return fail("gemm: this layer cannot normalise its output in the epilogue");
@@ -361,8 +363,9 @@ cudaError_t launch_gemm(const GemmDesc& d, cudaStream_t stream, std::string* err
     const int units = resident_units(pair);
     if (pair) grid = 2 * (int)(total < units ? total : units);
     else grid = (int)(total < units ? total : units);
-    const int span = p.tiles_per_img * (pair ? (p.num_n_tiles + 1) / 2 : p.num_n_tiles);
+    const int span = p.num_par * p.tiles_per_img * (pair ? (p.num_n_tiles + 1) / 2 : p.num_n_tiles);
     if (span > (pair ? grid / 2 : grid)) return fail("gemm: an image spans more tiles than there are resident CTAs");
+    if (p.tiles_per_img * 2 * p.num_par > 255) return fail("gemm: more than 255 statistics contributions per image");
     // RGM_GN_ALIGN=1 rounds the grid down to whole images per wave (no image straddles two waves of the grid).  Measured
     // (profiles/r2_trace_conv_norm.txt): not worth the idle CTAs -- 0.599 vs 0.597 ms at 128 -> 128 @ 128x128 (128 of
     // 148 CTAs), 0.499 vs 0.474 ms at 256 -> 256 @ 64x64 (64 of 74 pairs) -- so it is off.
@@ -376,7 +379,7 @@ cudaError_t launch_gemm(const GemmDesc& d, cudaStream_t stream, std::string* err
       grid = pair ? 2 * g : g;
     }
     p.band_n = 0;
-    p.epi.gn_inv_count = 1.0f / ((float)(oH * oW) * (float)(d.N / 32));
+    p.epi.gn_inv_count = 1.0f / ((float)(p.num_par * oH * oW) * (float)(d.N / 32));
   }
 
   // profiling label: conv kind, K, N and epilogue identify the layer family; flops_alg counts the reference's
@@ -420,22 +423,28 @@ cudaError_t launch_gemm(const GemmDesc& d, cudaStream_t stream, std::string* err
 
 // Layers whose epilogue can normalise their own output (gn_epilogue_loop); the same geometry as launch_gemm.
 bool gemm_gn_fuse_supported(const GemmDesc& d) {
-  if (d.conv != CONV_3x3 && d.conv != CONV_1x1) return false;
+  const bool up = d.conv == CONV_UP2;  // (dual form only: the caller passes EpiParams::gn_out2)
+  if (d.conv != CONV_3x3 && d.conv != CONV_1x1 && !up) return false;
+  if (up) {
+    const char* pf = getenv("RGM_PAR_FAST");
+    if (d.W % 32 != 0 || (pf && atoi(pf) == 0)) return false;
+  }
   // 32 groups of 4, 8 or 16 channels: whole channel quads per group, groups inside one warp's 32 features
   if (d.epi != EPI_F16 || (d.N != 128 && d.N != 256 && d.N != 512) || d.b_batch > 1 || d.block_n == 32) return false;
-  if (d.e.addtab != nullptr || d.e.up2 || d.e.act != ACT_NONE) return false;  // (a residual needs the dual form)
+  if (d.e.addtab != nullptr || d.e.act != ACT_NONE) return false;  // (a residual needs the dual form)
   if (d.H < 2 || d.W > SW_ROWS || SW_ROWS % d.W != 0) return false;
   const long long HW = (long long)d.H * d.W;
   if (HW % SW_ROWS != 0) return false;
   const int tiles_per_img = (int)(HW / SW_ROWS), n_tiles = d.N / SW_FEATS;
+  const int npar = up ? 4 : 1;
   const long long num_m = (long long)d.n_img * tiles_per_img;
-  const long long pair_tiles = num_m * ((n_tiles + 1) / 2);
+  const long long pair_tiles = num_m * ((n_tiles + 1) / 2) * npar;
   const bool pair = pair_mode_enabled() && n_tiles >= 2 && pair_tiles >= device_sm_count() / 2;
-  const long long total = pair ? pair_tiles : num_m * n_tiles;
+  const long long total = pair ? pair_tiles : num_m * n_tiles * npar;
   const int units = resident_units(pair);
   const long long g = total < units ? total : units;
-  const int span = tiles_per_img * (pair ? (n_tiles + 1) / 2 : n_tiles);
-  return span <= g;
+  const int span = npar * tiles_per_img * (pair ? (n_tiles + 1) / 2 : n_tiles);
+  return span <= g && tiles_per_img * 2 * npar <= 255;
 }
 
 // shape test: layers the fused kernel can run

@@ -818,7 +818,7 @@ __device__ __forceinline__ bool gn_ready(const GemmParams& p, int m_tile, int n_
   const EpiParams& e = p.epi;
   const int n = n_tile * SW_FEATS + quad * 32 + lane;
   const int img = m_tile / p.tiles_per_img;
-  const unsigned spi = (unsigned)p.tiles_per_img * 2u;
+  const unsigned spi = (unsigned)(p.tiles_per_img * 2 * p.num_par);  // contributions per (image, group)
   const unsigned long long* gsum = e.gn_sums + ((long long)img * 32 + n / (p.N >> 5)) * 2;
   w0 = ld_relaxed_gpu_u64(gsum);
   w1 = ld_relaxed_gpu_u64(gsum + 1);
@@ -934,7 +934,8 @@ __device__ __forceinline__ void gn_dual_cols(const __half* ip, __half* op, int l
   }
 }
 
-__device__ __forceinline__ void gn_dual_pass2(const GemmParams& p, int m_tile, int n_tile, int quad, int rhalf, int lane) {
+__device__ __forceinline__ void gn_dual_pass2(const GemmParams& p, int m_tile, int n_tile, int par, int quad, int rhalf,
+                                              int lane) {
   const EpiParams& e = p.epi;
   const int n = n_tile * SW_FEATS + quad * 32 + lane;
   const float gamma = __ldg(e.gn_gamma + n), beta = __ldg(e.gn_beta + n);
@@ -948,10 +949,25 @@ __device__ __forceinline__ void gn_dual_pass2(const GemmParams& p, int m_tile, i
   }
   float a, b;
   gn_affine(e, w0, w1, gamma, beta, a, b);
+  const bool sw = e.gn_swish != 0;
+  if (e.up2) {
+    // upsample conv: the 32 low-resolution pixels of a round (one image row segment: upW % 32 == 0) land on every
+    // second pixel of output row 2h + (par >> 1), starting at column 2w + (par & 1) (sw_epilogue_tile's mapping)
+    const int hw = e.upH * e.upW;
+#pragma unroll 1
+    for (int c = 0; c < 128; c += 32) {
+      const int row0 = m_tile * SW_ROWS + rhalf * 128 + c;
+      const int im = row0 / hw, rem = row0 - im * hw;
+      const int h = rem / e.upW, w = rem - h * e.upW;
+      const long long orow0 = ((long long)im * (2 * e.upH) + (2 * h + (par >> 1))) * (2 * e.upW) + (2 * w + (par & 1));
+      const long long o = orow0 * e.ldo + n;
+      gn_dual_cols<0>(static_cast<const __half*>(e.out) + o, e.gn_out2 + o, 2 * e.ldo, a, b, sw);
+    }
+    return;
+  }
   const long long off = (long long)(m_tile * SW_ROWS + rhalf * 128) * e.ldo + n;
   const __half* ip = static_cast<const __half*>(e.out) + off;
   __half* op = e.gn_out2 + off;
-  const bool sw = e.gn_swish != 0;
 #pragma unroll 1
   for (int c = 0; c < 128; c += 32) {
     const long long o = (long long)c * e.ldo;
@@ -968,24 +984,25 @@ template <class Coords, class Release>
 __device__ __forceinline__ void gn_dual_loop(const GemmParams& p, uint32_t tmem_base, uint64_t* tmem_full, int first,
                                              int stride, int total, int quad, int rhalf, int lane, Coords coords,
                                              Release release) {
-  int pm = -1, pn = 0;  // the tile whose normalised copy is still owed
+  int pm = -1, pn = 0, pp = 0;  // the tile whose normalised copy is still owed
   int k = 0;
   for (int t = first; t < total; t += stride, ++k) {
-    int m_tile, n_tile;
-    coords(t, m_tile, n_tile);
+    int m_tile, n_tile, par;
+    coords(t, m_tile, n_tile, par);
     mbar_wait(&tmem_full[k & 1], (k >> 1) & 1);
     tc_fence_after();
     float2 st = make_float2(0.f, 0.f);
-    sw_epilogue_tile<EPI_F16>(p, tmem_base + (k & 1) * SW_ROWS, m_tile, n_tile, 0, quad, rhalf, lane, &st);
+    sw_epilogue_tile<EPI_F16>(p, tmem_base + (k & 1) * SW_ROWS, m_tile, n_tile, par, quad, rhalf, lane, &st);
     tc_fence_before();
     __syncwarp();
     if (lane == 0) release(k & 1);
     gn_publish(p, m_tile, n_tile, quad, lane, st.x, st.y);
-    if (pm >= 0) gn_dual_pass2(p, pm, pn, quad, rhalf, lane);
+    if (pm >= 0) gn_dual_pass2(p, pm, pn, pp, quad, rhalf, lane);
     pm = m_tile;
     pn = n_tile;
+    pp = par;
   }
-  if (pm >= 0) gn_dual_pass2(p, pm, pn, quad, rhalf, lane);
+  if (pm >= 0) gn_dual_pass2(p, pm, pn, pp, quad, rhalf, lane);
 }
 
 template <int EPI>
@@ -1108,9 +1125,11 @@ gemm_sw_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
     if (EPI == EPI_F16 && p.epi.gn_sums != nullptr && p.epi.gn_out2 != nullptr) {
       gn_dual_loop(
           p, tmem_base, tmem_full, blockIdx.x, gridDim.x, total_tiles, quad, rhalf, lane,
-          [&](int t, int& m_tile, int& n_tile) {
-            m_tile = t / p.num_n_tiles;
-            n_tile = t - m_tile * p.num_n_tiles;
+          [&](int t, int& m_tile, int& n_tile, int& par) {
+            int tt;
+            split_parity(t, p.num_par, tiles_mn, p.par_fast != 0, par, tt);
+            m_tile = tt / p.num_n_tiles;
+            n_tile = tt - m_tile * p.num_n_tiles;
           },
           [&](int a) { mbar_arrive(&tmem_empty[a]); });
     } else if (EPI == EPI_F16 && p.epi.gn_sums != nullptr) {  // (num_par == 1 in this mode)
@@ -1319,9 +1338,10 @@ gemm_sw2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
     if (EPI == EPI_F16 && p.epi.gn_sums != nullptr && p.epi.gn_out2 != nullptr) {
       gn_dual_loop(
           p, tmem_base, tmem_full, pair_id, num_pairs, total_tiles, quad, rhalf, lane,
-          [&](int t, int& m_tile, int& n_tile) {
-            int n_pair;
-            sw2_tile_coords(t, p.num_m_tiles, pairs_n, p.band_n, m_tile, n_pair);
+          [&](int t, int& m_tile, int& n_tile, int& par) {
+            int tt, n_pair;
+            split_parity(t, p.num_par, tiles_mn, p.par_fast != 0, par, tt);
+            sw2_tile_coords(tt, p.num_m_tiles, pairs_n, p.band_n, m_tile, n_pair);
             n_tile = 2 * n_pair + (int)rank;
           },
           [&](int a) {

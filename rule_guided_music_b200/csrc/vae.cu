@@ -91,6 +91,10 @@ struct Vae {
   // conv1 of a ResnetBlock applies norm2 + swish to its own output inside its epilogue (gemm_tc.cuh,
   // gn_epilogue_loop): RGM_GN_EPI=0 restores the separate normalise pass
   bool gn_epi = true;
+  // ... and conv2 / proj_out write the raw tensor AND its copy normalised for the next block ("dual" form): RGM_GN_DUAL=0
+  // keeps the separate pass for those.  The upsample convs can do the same (RGM_GN_DUAL_UP=1) but lose: with K = 1024 the
+  // mainloop is shorter than the two-pass epilogue (measured 1.62 vs 0.99 + 0.43 ms per 64x64 -> 128x128 launch).
+  bool gn_dual = true, gn_dual_up = false;
   int* gn_err = nullptr;  // device flag: a GroupNorm-in-epilogue wait gave up (rgm_vae_gn_timeouts)
 
   ~Vae() {
@@ -392,7 +396,7 @@ int run_res(Ctx& c, const Res& r, __half* const* buf, Act& a, int H, const Norm*
     if (run_conv(c, r.nin, x, H, nullptr, buf[o], nullptr)) return -1;
     resid = buf[o];  // conv2 adds the shortcut it finds in `out` and overwrites it (same thread reads then writes)
   }
-  const bool dual = next != nullptr && want_copy && can_fuse_out_norm(c, r.c2, H);
+  const bool dual = next != nullptr && want_copy && c.m->gn_dual && can_fuse_out_norm(c, r.c2, H);
   const int on = dual ? take_free(used) : -1;  // x, conv2's input and the output are live: the fourth buffer is free
   if (run_conv(c, r.c2, buf[in2], H, resid, buf[o], dual ? nullptr : next, f2, dual ? next : nullptr,
                dual ? buf[on] : nullptr, next_swish))
@@ -477,7 +481,7 @@ int run_mid_attn(Ctx& c, const Norm& norm, const Conv& cq, const Conv& ck, const
     RGM_VGEMM_OK(d);
   }
   // x + proj_out(attention) over the (dead) normalised input; q / k / v are dead too: their buffer takes the copy
-  const bool dual = next != nullptr && can_fuse_out_norm(c, cproj, H);
+  const bool dual = next != nullptr && c.m->gn_dual && can_fuse_out_norm(c, cproj, H);
   if (run_conv(c, cproj, ao, H, x, hn, dual ? nullptr : next, false, dual ? next : nullptr, dual ? buf[b1] : nullptr, true))
     return -1;
   a.x = ihn;
@@ -511,10 +515,14 @@ int decode_chunk(Vae* m, Vae::Lane* L, const float* lat, float scale, float* rol
       if (run_res(c, m->up[lvl][b], buf, a, H, next, true, /*want_copy=*/!last)) return -1;
     }
     if (lvl != 0) {
-      const int o = (a.x + 1) & 3;  // (a.xn is -1 here)
-      if (run_conv(c, m->upsample[lvl], buf[a.x], H, nullptr, buf[o], &m->up[lvl - 1][0].n1)) return -1;
+      const int o = (a.x + 1) & 3, on = (a.x + 2) & 3;  // (a.xn is -1 here)
+      const Norm* next = &m->up[lvl - 1][0].n1;
+      const bool dual = m->gn_dual_up && can_fuse_out_norm(c, m->upsample[lvl], H);  // (off: see Vae::gn_dual_up)
+      if (run_conv(c, m->upsample[lvl], buf[a.x], H, nullptr, buf[o], dual ? nullptr : next, false, dual ? next : nullptr,
+                   dual ? buf[on] : nullptr, true))
+        return -1;
       a.x = o;
-      a.xn = -1;
+      a.xn = dual ? on : -1;
       H *= 2;
     }
   }
@@ -653,6 +661,8 @@ int rgm_vae_create(rgm_vae** out, int ch, const int* ch_mult, int n_levels, int 
   if (const char* e = getenv("RGM_VAE_CHUNK")) m->chunk_tiles = atoi(e) > 0 ? atoi(e) : m->chunk_tiles;
   if (const char* e = getenv("RGM_VAE_LANES")) m->n_lanes = atoi(e) >= 2 ? 2 : 1;
   if (const char* e = getenv("RGM_GN_EPI")) m->gn_epi = atoi(e) != 0;
+  if (const char* e = getenv("RGM_GN_DUAL")) m->gn_dual = atoi(e) != 0;
+  if (const char* e = getenv("RGM_GN_DUAL_UP")) m->gn_dual_up = atoi(e) != 0;
   if (vae_build(m) != 0) {
     delete m;
     return -1;

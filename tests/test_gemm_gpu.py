@@ -267,3 +267,44 @@ def test_conv_dual_raw_and_normalised_output(cuda, n, H, cin, cout, resid):
     assert (d > 0).float().mean().item() < 0.02   # same inputs, statistics equal to ~1e-6: rare last-bit differences
     ref = F.silu(F.group_norm(conv, 32, gamma, beta, eps=1e-6)).permute(0, 2, 3, 1)
     assert (out.float() - ref).abs().max().item() <= 3e-3 * ref.abs().max().item() + 1e-3
+
+
+@pytest.mark.parametrize("n,H,c", [(6, 32, 256), (20, 64, 256)])
+def test_upsample_conv_dual_raw_and_normalised_output(cuda, n, H, c):
+    """The nearest-2x-upsample + 3x3 conv (four parity sub-convolutions) in the dual form: raw output bit-identical to
+    the plain launch, normalised copy = this library's normalise pass on it up to rare last-bit differences."""
+    g = torch.Generator(device="cpu").manual_seed(n + H + c)
+    x = (torch.randn(n, H, H, c, generator=g) * 1.1).to(cuda).half()
+    w = (torch.randn(c, c, 3, 3, generator=g) / (c * 9) ** 0.5).to(cuda)
+    bias = torch.randn(c, generator=g).to(cuda)
+    gamma = (torch.rand(c, generator=g) + 0.5).to(cuda)
+    beta = (torch.randn(c, generator=g) * 0.3).to(cuda)
+    wp = _pack(w, 2)
+    plain = _conv(x, wp, bias, c, 2)
+    scratch = torch.full((n * 128,), -1, device=cuda, dtype=torch.int32)
+    err = torch.zeros(1, device=cuda, dtype=torch.int32)
+    raw = torch.empty_like(plain)
+    out = torch.empty_like(plain)
+    _lib.call("rgm_conv_norm_f16", _lib.ptr(x), _lib.ptr(wp), _lib.ptr(bias), _lib.ptr(gamma), _lib.ptr(beta), None,
+              _lib.ptr(raw), _lib.ptr(out), n, H, H, c, c, 2, 1, _lib.ptr(scratch), _lib.ptr(err), _lib.stream_ptr())
+    torch.cuda.synchronize()
+    assert err.item() == 0, "a GroupNorm-in-epilogue wait gave up"
+    assert torch.equal(raw, plain)
+    count = scratch.view(n, 64, 2)[:, :, 0] & 255
+    assert int(count.min()) == int(count.max()) == 2 * 4 * (H * H // 256)
+    conv = F.conv2d(F.interpolate(x.float().permute(0, 3, 1, 2), scale_factor=2.0, mode="nearest"), w.half().float(), bias,
+                    padding=1)
+    ref = F.silu(F.group_norm(conv, 32, gamma, beta, eps=1e-6)).permute(0, 2, 3, 1)
+    assert (out.float() - ref).abs().max().item() <= 6e-3 * ref.abs().max().item() + 1e-3
+    cpg = c // 32
+    r32 = raw.float().reshape(n, 4 * H * H, 32, cpg)
+    mean = r32.mean(dim=(1, 3))
+    rstd = (r32.var(dim=(1, 3), unbiased=False) + 1e-6).rsqrt()
+    a = rstd.repeat_interleave(cpg, dim=1) * gamma
+    b = beta - mean.repeat_interleave(cpg, dim=1) * a
+    two = torch.empty_like(out)
+    ab = torch.stack((a, b), dim=-1).contiguous()
+    _lib.call("rgm_gn_apply_f16", _lib.ptr(raw), _lib.ptr(ab), _lib.ptr(two), n, 4 * H * H, c, 1, _lib.stream_ptr())
+    torch.cuda.synchronize()
+    d = (out.float() - two.float()).abs()
+    assert d.max().item() <= 3e-3 * two.float().abs().max().item() + 1e-3, d.max().item()

@@ -391,7 +391,7 @@ cudaError_t launch_gemm(const GemmDesc& d, cudaStream_t stream, std::string* err
   const double f_alg = d.conv == CONV_UP2 ? 2.0 * rows * d.N * 9.0 * d.C : f_exec;
   if (g_prof_on.load(std::memory_order_relaxed))
     snprintf(pname, sizeof pname, "gemm_tc conv%d H%d K%d N%d epi%d %s%s", d.conv, d.H, (int)Kexec, d.N, d.epi,
-             pair ? "f256xr256 pair" : (sw ? "f128xr256" : "r128xf32"), gn_fuse ? " +norm" : "");
+             pair ? "f256xr256 pair" : (sw ? "f128xr256" : "r128xf32"), gn_fuse ? (d.e.gn_out2 != nullptr ? " +raw+norm" : " +norm") : "");
   ProfScope prof(pname, f_alg, f_exec, 0.0, stream);
 
   cudaError_t st = cudaErrorInvalidValue;

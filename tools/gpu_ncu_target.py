@@ -36,7 +36,23 @@ bg = torch.zeros(128, device=dev)
 og = torch.empty(n_cg, 128, 128, 128, device=dev, dtype=torch.float16)
 
 
+# convolutions that normalise their own output in the epilogue, at one bench chunk's shape: conv1 of a 128-wide block
+# (accumulators wait in tensor memory) and conv2 (dual form: raw + residual and the normalised copy)
+gam, bet = torch.ones(128, device=dev), torch.zeros(128, device=dev)
+scr = torch.zeros(n_cg * 128, device=dev, dtype=torch.int32)
+gerr = torch.zeros(1, device=dev, dtype=torch.int32)
+rawg = torch.empty_like(og)
+
+
 def run():
+    if part in ("convnorm",):
+        _lib.call("rgm_conv_norm_f16", _lib.ptr(xg), _lib.ptr(wg), _lib.ptr(bg), _lib.ptr(gam), _lib.ptr(bet), None, None,
+                  _lib.ptr(og), n_cg, 128, 128, cin, 128, 1, 1, _lib.ptr(scr), _lib.ptr(gerr), _lib.stream_ptr())
+        _lib.call("rgm_conv_norm_f16", _lib.ptr(xg), _lib.ptr(wg), _lib.ptr(bg), _lib.ptr(gam), _lib.ptr(bet), _lib.ptr(xg),
+                  _lib.ptr(rawg), _lib.ptr(og), n_cg, 128, 128, cin, 128, 1, 1, _lib.ptr(scr), _lib.ptr(gerr),
+                  _lib.stream_ptr())
+        _lib.call("rgm_conv_f16", _lib.ptr(xg), _lib.ptr(wg), _lib.ptr(bg), None, _lib.ptr(og), n_cg, 128, 128, cin, 128, 1, 0,
+                  None, _lib.stream_ptr())
     if part in ("dit", "all"):
         model(x, t, y)
     if part in ("vae", "all"):

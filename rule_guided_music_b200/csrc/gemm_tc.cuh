@@ -782,14 +782,25 @@ __device__ __forceinline__ void gn_pass1(const GemmParams& p, uint32_t tmem_acc,
   const int n = n_tile * SW_FEATS + quad * 32 + lane;  // this thread's output feature
   const float bias = e.bias ? __ldg(e.bias + n) : 0.f;
   float gs = 0.f, gq = 0.f;  // from the fp32 values (the host guarantees M % 256 == 0: every row is valid)
-#pragma unroll 1
-  for (int c = 0; c < 128; c += 32) {
-    uint32_t r[32];
-    tmem_ld_32x32(taddr + c, r);
+  // the load of the next 32 columns is in flight while these 32 are summed (tcgen05.ld latency x 4 is otherwise exposed:
+  // this pass sits on the critical path of the tile)
+  uint32_t ra[32], rb[32];
+  tmem_ld_32x32(taddr, ra);
+#pragma unroll
+  for (int c = 0; c < 128; c += 64) {
     tmem_ld_wait();
+    tmem_ld_32x32(taddr + c + 32, rb);
 #pragma unroll
     for (int j = 0; j < 32; ++j) {
-      const float x = fmaf(__uint_as_float(r[j]), e.alpha, bias);
+      const float x = fmaf(__uint_as_float(ra[j]), e.alpha, bias);
+      gs += x;
+      gq = fmaf(x, x, gq);
+    }
+    tmem_ld_wait();
+    if (c + 64 < 128) tmem_ld_32x32(taddr + c + 64, ra);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const float x = fmaf(__uint_as_float(rb[j]), e.alpha, bias);
       gs += x;
       gq = fmaf(x, x, gq);
     }
@@ -841,11 +852,7 @@ __device__ __forceinline__ void gn_pass2(const GemmParams& p, uint32_t tmem_acc,
   gn_affine(e, w0, w1, gamma, beta, a, b);
   __half* op = static_cast<__half*>(e.out) + (long long)rbase * e.ldo + n;
   const bool sw = e.gn_swish != 0;
-#pragma unroll 1
-  for (int c = 0; c < 128; c += 32) {
-    uint32_t r[32];
-    tmem_ld_32x32(taddr + c, r);
-    tmem_ld_wait();
+  auto store = [&](const uint32_t (&r)[32], int c) {
     __half* oc = op + (long long)c * e.ldo;
     switch (e.ldo) {
       case 128: gn_store_cols<128>(r, oc, e.ldo, e.alpha, bias, a, b, sw); break;
@@ -853,6 +860,17 @@ __device__ __forceinline__ void gn_pass2(const GemmParams& p, uint32_t tmem_acc,
       case 512: gn_store_cols<512>(r, oc, e.ldo, e.alpha, bias, a, b, sw); break;
       default: gn_store_cols<0>(r, oc, e.ldo, e.alpha, bias, a, b, sw); break;
     }
+  };
+  uint32_t ra[32], rb[32];  // the next 32 columns are in flight while these are normalised and stored
+  tmem_ld_32x32(taddr, ra);
+#pragma unroll 1
+  for (int c = 0; c < 128; c += 64) {
+    tmem_ld_wait();
+    tmem_ld_32x32(taddr + c + 32, rb);
+    store(ra, c);
+    tmem_ld_wait();
+    if (c + 64 < 128) tmem_ld_32x32(taddr + c + 64, ra);
+    store(rb, c + 32);
   }
   if (tr && lane == 0) tr[5] = clock64();
 }
@@ -920,9 +938,34 @@ __device__ __forceinline__ void gn_epilogue_loop(const GemmParams& p, uint32_t t
 // image's other tiles have contributed (no idle wait), and the warp re-reads its own 32 features x 128 rows -- still
 // in L2 -- normalises them and stores them to gn_out2.  Compared with the separate pass this saves the DRAM read of
 // the raw tensor and a launch, and never holds tensor memory.
+// all 128 rows of the warp: the 32 loads of the next round are issued before this round is normalised and stored (an L2
+// round trip per round would otherwise be exposed four times per tile)
 template <int LDO>
-__device__ __forceinline__ void gn_dual_cols(const __half* ip, __half* op, int ldo_dyn, float a, float b, bool swish) {
+__device__ __forceinline__ void gn_dual_cols(const __half* ip, __half* op, int ldo_dyn, long long round_stride, float a,
+                                             float b, bool swish) {
   const int ldo = LDO > 0 ? LDO : ldo_dyn;
+  __half v[2][32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) v[0][j] = __ldcg(ip + j * ldo);
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    if (c + 1 < 4) {
+      const __half* in = ip + (c + 1) * round_stride;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[(c + 1) & 1][j] = __ldcg(in + j * ldo);
+    }
+    __half* oc = op + c * round_stride;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      float y = fmaf(a, __half2float(v[c & 1][j]), b);
+      if (swish) y = silu_f(y);
+      oc[j * ldo] = __float2half_rn(y);
+    }
+  }
+}
+
+// one round of 32 rows (the upsample conv's scattered rows)
+__device__ __forceinline__ void gn_dual_round(const __half* ip, __half* op, int ldo, float a, float b, bool swish) {
   __half v[32];
 #pragma unroll
   for (int j = 0; j < 32; ++j) v[j] = __ldcg(ip + j * ldo);
@@ -961,22 +1004,19 @@ __device__ __forceinline__ void gn_dual_pass2(const GemmParams& p, int m_tile, i
       const int h = rem / e.upW, w = rem - h * e.upW;
       const long long orow0 = ((long long)im * (2 * e.upH) + (2 * h + (par >> 1))) * (2 * e.upW) + (2 * w + (par & 1));
       const long long o = orow0 * e.ldo + n;
-      gn_dual_cols<0>(static_cast<const __half*>(e.out) + o, e.gn_out2 + o, 2 * e.ldo, a, b, sw);
+      gn_dual_round(static_cast<const __half*>(e.out) + o, e.gn_out2 + o, 2 * e.ldo, a, b, sw);
     }
     return;
   }
   const long long off = (long long)(m_tile * SW_ROWS + rhalf * 128) * e.ldo + n;
   const __half* ip = static_cast<const __half*>(e.out) + off;
   __half* op = e.gn_out2 + off;
-#pragma unroll 1
-  for (int c = 0; c < 128; c += 32) {
-    const long long o = (long long)c * e.ldo;
-    switch (e.ldo) {
-      case 128: gn_dual_cols<128>(ip + o, op + o, e.ldo, a, b, sw); break;
-      case 256: gn_dual_cols<256>(ip + o, op + o, e.ldo, a, b, sw); break;
-      case 512: gn_dual_cols<512>(ip + o, op + o, e.ldo, a, b, sw); break;
-      default: gn_dual_cols<0>(ip + o, op + o, e.ldo, a, b, sw); break;
-    }
+  const long long rs = 32LL * e.ldo;
+  switch (e.ldo) {
+    case 128: gn_dual_cols<128>(ip, op, e.ldo, rs, a, b, sw); break;
+    case 256: gn_dual_cols<256>(ip, op, e.ldo, rs, a, b, sw); break;
+    case 512: gn_dual_cols<512>(ip, op, e.ldo, rs, a, b, sw); break;
+    default: gn_dual_cols<0>(ip, op, e.ldo, rs, a, b, sw); break;
   }
 }
 

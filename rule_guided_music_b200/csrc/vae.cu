@@ -396,7 +396,10 @@ int run_res(Ctx& c, const Res& r, __half* const* buf, Act& a, int H, const Norm*
     if (run_conv(c, r.nin, x, H, nullptr, buf[o], nullptr)) return -1;
     resid = buf[o];  // conv2 adds the shortcut it finds in `out` and overwrites it (same thread reads then writes)
   }
-  const bool dual = next != nullptr && want_copy && c.m->gn_dual && can_fuse_out_norm(c, r.c2, H);
+  // (not for the 128-feature convolutions: their K = 1152 mainloop on one CTA is shorter than the two-pass epilogue --
+  // measured in the step 0.90 ms against 0.58 + 0.22 ms for convolution + normalise pass; the 256- and 512-feature
+  // layers on CTA pairs gain 0.06 / 0.015 / 0.006 ms per launch)
+  const bool dual = next != nullptr && want_copy && c.m->gn_dual && r.c2.cout >= 256 && can_fuse_out_norm(c, r.c2, H);
   const int on = dual ? take_free(used) : -1;  // x, conv2's input and the output are live: the fourth buffer is free
   if (run_conv(c, r.c2, buf[in2], H, resid, buf[o], dual ? nullptr : next, f2, dual ? next : nullptr,
                dual ? buf[on] : nullptr, next_swish))

@@ -95,10 +95,15 @@ struct Vae {
   // keeps the separate pass for those.  The upsample convs can do the same (RGM_GN_DUAL_UP=1) but lose: with K = 1024 the
   // mainloop is shorter than the two-pass epilogue (measured 1.62 vs 0.99 + 0.43 ms per 64x64 -> 128x128 launch).
   bool gn_dual = true, gn_dual_up = false;
-  int* gn_err = nullptr;  // device flag: a GroupNorm-in-epilogue wait gave up (rgm_vae_gn_timeouts)
+  // flag "a GroupNorm-in-epilogue wait gave up" in pinned, mapped host memory: the kernels write it through gn_err (the
+  // device alias), the host reads gn_err_h without a synchronisation at the start of every decode / encode call, so a
+  // run that produced garbage fails loudly at the next call (and rgm_vae_gn_timeouts reports it after a sync)
+  int* gn_err = nullptr;
+  int* gn_err_h = nullptr;
 
   ~Vae() {
     for (void* p : allocs) cudaFree(p);
+    if (gn_err_h) cudaFreeHost(gn_err_h);
     for (auto& l : lane) {
       if (l.stream) cudaStreamDestroy(l.stream);
       if (l.done) cudaEventDestroy(l.done);
@@ -182,7 +187,10 @@ int vae_build(Vae* m) {
                         CONV_UP2);
   }
   ok = ok && m->make_norm(m->norm_out, "decoder.norm_out", block_in);
-  m->gn_err = m->alloc<int>(1);
+  if (cudaHostAlloc(reinterpret_cast<void**>(&m->gn_err_h), sizeof(int), cudaHostAllocMapped) == cudaSuccess) {
+    *m->gn_err_h = 0;
+    if (cudaHostGetDevicePointer(reinterpret_cast<void**>(&m->gn_err), m->gn_err_h, 0) != cudaSuccess) m->gn_err = nullptr;
+  }
   ok = ok && m->gn_err != nullptr;
   m->cout_cin = block_in;
   m->cout_w = m->alloc<float>((long long)m->out_ch * block_in * 9);
@@ -692,11 +700,8 @@ int rgm_vae_reserve(rgm_vae* h, int n_tiles) {
 int rgm_vae_gn_timeouts(rgm_vae* h) {
   if (!h) return set_error("rgm_vae_gn_timeouts: null handle");
   Vae* m = reinterpret_cast<Vae*>(h);
-  int v = 0;
-  if (cudaDeviceSynchronize() != cudaSuccess ||
-      cudaMemcpy(&v, m->gn_err, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess)
-    return set_error("rgm_vae_gn_timeouts: device error");
-  return v;
+  if (cudaDeviceSynchronize() != cudaSuccess) return set_error("rgm_vae_gn_timeouts: device error");
+  return *static_cast<volatile int*>(m->gn_err_h);
 }
 
 int rgm_vae_destroy(rgm_vae* h) {
@@ -734,6 +739,8 @@ int rgm_vae_encode(rgm_vae* h, const float* x, float* moments, int n, void* stre
   if (!h || !x || !moments) return set_error("rgm_vae_encode: null argument");
   Vae* m = reinterpret_cast<Vae*>(h);
   if (n <= 0) return 0;
+  if (*static_cast<volatile int*>(m->gn_err_h))
+    return set_error("rgm_vae_encode: an earlier call's GroupNorm-in-epilogue wait gave up (its results are invalid)");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int chunk = m->chunk_tiles < n ? m->chunk_tiles : n;
   if (vae_reserve(m, chunk, 1, st) != 0) return -1;
@@ -753,6 +760,8 @@ int rgm_vae_decode_latents(rgm_vae* h, const float* lat, float scale_factor, flo
   if (n_cand <= 0) return 0;
   if (Hlat % 16 != 0 || Hlat <= 0) return set_error("rgm_vae_decode_latents: latent length must be a multiple of 16");
   if (roll_ch < 1 || roll_ch > m->out_ch) return set_error("rgm_vae_decode_latents: roll_ch out of range");
+  if (*static_cast<volatile int*>(m->gn_err_h))
+    return set_error("rgm_vae_decode_latents: an earlier call's GroupNorm-in-epilogue wait gave up (its results are invalid)");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int total = n_cand * (Hlat / 16);
   const int chunk = m->chunk_tiles < total ? m->chunk_tiles : total;

@@ -7,7 +7,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "librgm_b200.so")
+# RGM_LIB: an experiment build of the same library (csrc/Makefile EXTRA / OUT), for A/B measurements by the tools
+LIB_PATH = os.environ.get("RGM_LIB") or os.path.join(_HERE, "librgm_b200.so")
 
 _lib = None
 

@@ -13,7 +13,7 @@
 namespace rgm {
 
 // x * sigmoid(x) in 5 issue slots (ptx.cuh silu_f): the GroupNorm passes are ISSUE-bound, not MUFU- or HBM-bound.
-__device__ __forceinline__ float swish_fast(float v) { return silu_f(v); }
+__device__ __forceinline__ float swish_fast(float v) { return swish_vae(v); }
 
 namespace {
 std::atomic<unsigned long long> g_launches{0};

@@ -256,8 +256,8 @@ conv_gn_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
                 const float2 f = __half22float2(h2[j]);
-                const float v0 = silu_f(fmaf(a[2 * j], f.x, b[2 * j]));
-                const float v1 = silu_f(fmaf(a[2 * j + 1], f.y, b[2 * j + 1]));
+                const float v0 = swish_vae(fmaf(a[2 * j], f.x, b[2 * j]));
+                const float v1 = swish_vae(fmaf(a[2 * j + 1], f.y, b[2 * j + 1]));
                 h2[j] = __floats2half2_rn(v0, v1);
               }
               sts_v4(addr, u);

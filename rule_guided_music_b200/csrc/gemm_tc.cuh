@@ -745,7 +745,7 @@ __device__ __forceinline__ void gn_store_cols(const uint32_t (&r)[32], __half* o
 #pragma unroll
   for (int j = 0; j < 32; ++j) {
     float y = fmaf(a, fmaf(__uint_as_float(r[j]), alpha, bias), b);
-    if (swish) y = silu_f(y);
+    if (swish) y = swish_vae(y);
     op[j * ldo] = __float2half_rn(y);
   }
 }
@@ -958,7 +958,7 @@ __device__ __forceinline__ void gn_dual_cols(const __half* ip, __half* op, int l
 #pragma unroll
     for (int j = 0; j < 32; ++j) {
       float y = fmaf(a, __half2float(v[c & 1][j]), b);
-      if (swish) y = silu_f(y);
+      if (swish) y = swish_vae(y);
       oc[j * ldo] = __float2half_rn(y);
     }
   }
@@ -972,7 +972,7 @@ __device__ __forceinline__ void gn_dual_round(const __half* ip, __half* op, int 
 #pragma unroll
   for (int j = 0; j < 32; ++j) {
     float y = fmaf(a, __half2float(v[j]), b);
-    if (swish) y = silu_f(y);
+    if (swish) y = swish_vae(y);
     op[j * ldo] = __float2half_rn(y);
   }
 }

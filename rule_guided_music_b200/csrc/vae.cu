@@ -95,6 +95,7 @@ struct Vae {
   // keeps the separate pass for those.  The upsample convs can do the same (RGM_GN_DUAL_UP=1) but lose: with K = 1024 the
   // mainloop is shorter than the two-pass epilogue (measured 1.62 vs 0.99 + 0.43 ms per 64x64 -> 128x128 launch).
   bool gn_dual = true, gn_dual_up = false;
+  int gn_dual_min = 256;  // narrowest layer that uses the dual form (RGM_GN_DUAL_MIN)
   // flag "a GroupNorm-in-epilogue wait gave up" in pinned, mapped host memory: the kernels write it through gn_err (the
   // device alias), the host reads gn_err_h without a synchronisation at the start of every decode / encode call, so a
   // run that produced garbage fails loudly at the next call (and rgm_vae_gn_timeouts reports it after a sync)
@@ -407,7 +408,7 @@ int run_res(Ctx& c, const Res& r, __half* const* buf, Act& a, int H, const Norm*
   // (not for the 128-feature convolutions: their K = 1152 mainloop on one CTA is shorter than the two-pass epilogue --
   // measured in the step 0.90 ms against 0.58 + 0.22 ms for convolution + normalise pass; the 256- and 512-feature
   // layers on CTA pairs gain 0.06 / 0.015 / 0.006 ms per launch)
-  const bool dual = next != nullptr && want_copy && c.m->gn_dual && r.c2.cout >= 256 && can_fuse_out_norm(c, r.c2, H);
+  const bool dual = next != nullptr && want_copy && c.m->gn_dual && r.c2.cout >= c.m->gn_dual_min && can_fuse_out_norm(c, r.c2, H);
   const int on = dual ? take_free(used) : -1;  // x, conv2's input and the output are live: the fourth buffer is free
   if (run_conv(c, r.c2, buf[in2], H, resid, buf[o], dual ? nullptr : next, f2, dual ? next : nullptr,
                dual ? buf[on] : nullptr, next_swish))
@@ -674,6 +675,7 @@ int rgm_vae_create(rgm_vae** out, int ch, const int* ch_mult, int n_levels, int 
   if (const char* e = getenv("RGM_GN_EPI")) m->gn_epi = atoi(e) != 0;
   if (const char* e = getenv("RGM_GN_DUAL")) m->gn_dual = atoi(e) != 0;
   if (const char* e = getenv("RGM_GN_DUAL_UP")) m->gn_dual_up = atoi(e) != 0;
+  if (const char* e = getenv("RGM_GN_DUAL_MIN")) m->gn_dual_min = atoi(e);
   if (vae_build(m) != 0) {
     delete m;
     return -1;

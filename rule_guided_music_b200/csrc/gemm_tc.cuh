@@ -738,13 +738,14 @@ __device__ __forceinline__ void sw_epilogue_tile(const GemmParams& p, uint32_t t
 // co-resident and only layers whose images span at most `grid` consecutive tiles, so two tiles of one image never sit on
 // the same CTA and every wait is for tiles of the current or an earlier wave of other, running CTAs.  A wait that lasts
 // ~1 s gives up and raises gn_err instead of hanging the device.
+// y = swish(a2 r + b2) with the conv's alpha / bias folded into the GroupNorm affine by the caller
 template <int LDO>
-__device__ __forceinline__ void gn_store_cols(const uint32_t (&r)[32], __half* op, int ldo_dyn, float alpha, float bias,
-                                              float a, float b, bool swish) {
+__device__ __forceinline__ void gn_store_cols(const uint32_t (&r)[32], __half* op, int ldo_dyn, float a2, float b2,
+                                              bool swish) {
   const int ldo = LDO > 0 ? LDO : ldo_dyn;
 #pragma unroll
   for (int j = 0; j < 32; ++j) {
-    float y = fmaf(a, fmaf(__uint_as_float(r[j]), alpha, bias), b);
+    float y = fmaf(a2, __uint_as_float(r[j]), b2);
     if (swish) y = swish_vae(y);
     op[j * ldo] = __float2half_rn(y);
   }
@@ -781,9 +782,11 @@ __device__ __forceinline__ void gn_pass1(const GemmParams& p, uint32_t tmem_acc,
   const uint32_t taddr = tmem_acc + (static_cast<uint32_t>(quad * 32) << 16) + rhalf * 128;
   const int n = n_tile * SW_FEATS + quad * 32 + lane;  // this thread's output feature
   const float bias = e.bias ? __ldg(e.bias + n) : 0.f;
-  float gs = 0.f, gq = 0.f;  // from the fp32 values (the host guarantees M % 256 == 0: every row is valid)
-  // the load of the next 32 columns is in flight while these 32 are summed (tcgen05.ld latency x 4 is otherwise exposed:
-  // this pass sits on the critical path of the tile)
+  // Sums of the RAW accumulators r (two instructions per element); the statistics of x = alpha r + bias follow in closed
+  // form: sum x = alpha S + 128 bias, sum x^2 = alpha^2 Q + 2 alpha bias S + 128 bias^2.  (Every instruction of an
+  // epilogue is paid in clock on this power-bound part.)  The host guarantees M % 256 == 0: every row is valid.
+  // The load of the next 32 columns is in flight while these 32 are summed.
+  float rs = 0.f, rq = 0.f;
   uint32_t ra[32], rb[32];
   tmem_ld_32x32(taddr, ra);
 #pragma unroll
@@ -792,19 +795,22 @@ __device__ __forceinline__ void gn_pass1(const GemmParams& p, uint32_t tmem_acc,
     tmem_ld_32x32(taddr + c + 32, rb);
 #pragma unroll
     for (int j = 0; j < 32; ++j) {
-      const float x = fmaf(__uint_as_float(ra[j]), e.alpha, bias);
-      gs += x;
-      gq = fmaf(x, x, gq);
+      const float r = __uint_as_float(ra[j]);
+      rs += r;
+      rq = fmaf(r, r, rq);
     }
     tmem_ld_wait();
     if (c + 64 < 128) tmem_ld_32x32(taddr + c + 64, ra);
 #pragma unroll
     for (int j = 0; j < 32; ++j) {
-      const float x = fmaf(__uint_as_float(rb[j]), e.alpha, bias);
-      gs += x;
-      gq = fmaf(x, x, gq);
+      const float r = __uint_as_float(rb[j]);
+      rs += r;
+      rq = fmaf(r, r, rq);
     }
   }
+  const float ab2 = e.alpha * bias;
+  const float gs = fmaf(e.alpha, rs, 128.f * bias);
+  const float gq = fmaf(e.alpha * e.alpha, rq, fmaf(2.f * ab2, rs, 128.f * bias * bias));
   gn_publish(p, m_tile, n_tile, quad, lane, gs, gq);
   if (tr && lane == 0) tr[6] = clock64();  // statistics published
 }
@@ -852,13 +858,14 @@ __device__ __forceinline__ void gn_pass2(const GemmParams& p, uint32_t tmem_acc,
   gn_affine(e, w0, w1, gamma, beta, a, b);
   __half* op = static_cast<__half*>(e.out) + (long long)rbase * e.ldo + n;
   const bool sw = e.gn_swish != 0;
+  const float a2 = a * e.alpha, b2 = fmaf(a, bias, b);  // a (alpha r + bias) + b
   auto store = [&](const uint32_t (&r)[32], int c) {
     __half* oc = op + (long long)c * e.ldo;
     switch (e.ldo) {
-      case 128: gn_store_cols<128>(r, oc, e.ldo, e.alpha, bias, a, b, sw); break;
-      case 256: gn_store_cols<256>(r, oc, e.ldo, e.alpha, bias, a, b, sw); break;
-      case 512: gn_store_cols<512>(r, oc, e.ldo, e.alpha, bias, a, b, sw); break;
-      default: gn_store_cols<0>(r, oc, e.ldo, e.alpha, bias, a, b, sw); break;
+      case 128: gn_store_cols<128>(r, oc, e.ldo, a2, b2, sw); break;
+      case 256: gn_store_cols<256>(r, oc, e.ldo, a2, b2, sw); break;
+      case 512: gn_store_cols<512>(r, oc, e.ldo, a2, b2, sw); break;
+      default: gn_store_cols<0>(r, oc, e.ldo, a2, b2, sw); break;
     }
   };
   uint32_t ra[32], rb[32];  // the next 32 columns are in flight while these are normalised and stored

@@ -266,21 +266,13 @@ __device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
 }
 
 // ----------------------------------------------------------------------------------------------
-// device-scope release / acquire on a global counter: the per-image arrival counters of the GroupNorm-in-epilogue
-// convolutions (gemm_tc.cuh, gn_epilogue_loop).  The releasing lane's warp-mates order their own stores before it
-// with __syncwarp (causality order is cumulative); the acquiring lane's warp-mates read after a __syncwarp.
+// relaxed device-scope load: the lanes of the GroupNorm-in-epilogue convolutions poll their group's accumulator words
+// with it (gemm_tc.cuh, gn_ready).  No acquire is needed: a word carries its data AND its arrival count, so observing
+// the complete count is observing the complete sum (single-copy atomicity of the 64-bit word).
 // ----------------------------------------------------------------------------------------------
-__device__ __forceinline__ void red_release_gpu_add(int* p, int v) {
-  asm volatile("red.release.gpu.global.add.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
 __device__ __forceinline__ unsigned long long ld_relaxed_gpu_u64(const unsigned long long* p) {
   unsigned long long v;
   asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
-  int v;
-  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
 

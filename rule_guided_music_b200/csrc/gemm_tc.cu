@@ -180,14 +180,7 @@ int resident_units(bool pair) {
     }
     v = n < sms / 2 ? n : sms / 2;
   } else {
-    auto kern = gemm_sw_kernel<EPI_F16>;
-    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SW_SMEM_BYTES);
-    int n = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, GEMM_THREADS, SW_SMEM_BYTES) != cudaSuccess || n <= 0) {
-      cudaGetLastError();
-      n = 1;
-    }
-    v = sms;  // one CTA per SM is all the persistent kernel launches
+    v = sms;  // the single-CTA kernel launches at most one CTA per SM, and one always fits (198 KB of shared memory)
   }
   if (v < 1) v = 1;
   if (dev != 63) cache[dev][pair ? 1 : 0].store(v, std::memory_order_relaxed);

@@ -270,3 +270,13 @@ def test_decode_sample_for_midi_generic_branch_on_cpu():
     # boundary of the uint8 quantisation once in a while; never by more than one step
     diff = np.abs(got.astype(np.int16) - ref.astype(np.int16))
     assert diff.max() <= 1 and (diff != 0).mean() < 1e-3
+
+
+def test_vae_gn_timeouts_without_a_device_handle():
+    """The diagnostic accessor of the in-epilogue GroupNorm path must not need a device (or the library) before the
+    model has been moved to one."""
+    from rule_guided_music_b200.taming.models.klvae_pedal import AutoencoderKL
+    from oracle import weights as ow
+
+    v = AutoencoderKL(ddconfig=ow.VAE_DDCONFIG, embed_dim=4)
+    assert v.gn_timeouts() == 0

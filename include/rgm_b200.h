@@ -72,9 +72,11 @@ typedef struct rgm_vae rgm_vae;
 int rgm_vae_create(rgm_vae** out, int ch, const int* ch_mult_host, int n_levels, int num_res_blocks, int z_channels,
                    int out_ch);
 int rgm_vae_destroy(rgm_vae* h);
-/* Diagnostic: 1 if a convolution that normalises its own output (GroupNorm statistics exchanged between CTAs while the
- * accumulators wait in tensor memory) ever gave up waiting for its image's other tiles -- never in a healthy run; 0
- * otherwise; negative on error.  Synchronises the device. */
+/* Diagnostic of the convolutions that normalise their own output (GroupNorm statistics exchanged between CTAs while the
+ * accumulators wait in tensor memory): 0 in a healthy run; 1 if a wait for an image's other tiles ever gave up; 2 if a
+ * partial sum left the range of the fixed-point statistics (a GroupNorm group with an rms above ~250 over a whole image:
+ * create the handle with RGM_GN_EPI=0 for such weights); negative on error.  Synchronises the device.  After a non-zero
+ * value the handle's results are invalid and further decode / encode calls fail. */
 int rgm_vae_gn_timeouts(rgm_vae* h);
 /* Pre-size the activation buffers for decodes / encodes of up to n_tiles 16x16 latent tiles (same contract as
  * rgm_dit_reserve). */

@@ -60,7 +60,8 @@ struct EpiParams {
   // gn_epilogue_loop): when gn_sums != nullptr `out` receives swish(GroupNorm(conv(x))) and the raw tensor is never
   // written.  gn_sums: per-(image, group) accumulators [image][32][2] -- fixed-point sum / sum of squares in bits 63..8,
   // arrivals in bits 7..0 -- zeroed before the launch; gn_inv_count = 1 / (pixels x channels per group); gn_gamma /
-  // gn_beta: the norm's affine [N]; gn_err: set to 1 if a wait gives up (never in a healthy run)
+  // gn_beta: the norm's affine [N]; gn_err: set to 1 if a wait gives up, 2 if a partial sum leaves the fixed-point range
+  // (never in a healthy run)
   unsigned long long* gn_sums;
   float gn_inv_count;
   // "dual" form: `out` receives the RAW tensor as usual (residual allowed) and gn_out2 (same layout) the normalised copy
@@ -731,8 +732,8 @@ __device__ __forceinline__ void sw_epilogue_tile(const GemmParams& p, uint32_t t
 // 128 rows and adds them, as fixed-point integers that also count arrivals, to the image's per-group accumulators;
 // (2) the lanes poll their group's words until the image's other row tiles have contributed -- meanwhile the MMA warp is
 // filling the second accumulator buffer with the next tile; (3) the totals give the affine (integer sums: deterministic
-// whatever the arrival order); (4) a second pass over the same TMEM columns stores swish(a x + b) as fp16.  The raw convolution output is never written and never re-read:
-// per element one 2-byte store instead of store + load + store.
+// whatever the arrival order); (4) a second pass over the same TMEM columns stores swish(a x + b) as fp16.  The raw
+// convolution output is never written and never re-read: per element one 2-byte store instead of store + load + store.
 //
 // Progress: tiles are statically assigned (tile t -> CTA t mod grid), the host launches no more CTAs than are
 // co-resident and only layers whose images span at most `grid` consecutive tiles, so two tiles of one image never sit on
@@ -769,6 +770,9 @@ __device__ __forceinline__ void gn_publish(const GemmParams& p, int m_tile, int 
   const int img = m_tile / p.tiles_per_img;
   unsigned long long* gsum = e.gn_sums + ((long long)img * 32 + n / cpg) * 2;
   if ((lane & (cpg - 1)) == 0) {
+    // range of the 36.20 format with up to 255 contributions: a warp's partial must stay below 2^27 (a group whose
+    // values have an rms above ~250 over a whole image); beyond it the launch is flagged instead of wrapping silently
+    if (fabsf(gs) > 1.0e8f || gq > 1.0e8f) *e.gn_err = 2;
     atomicAdd(gsum, ((unsigned long long)__double2ll_rn((double)gs * 1048576.0) << 8) + 1ull);
     atomicAdd(gsum + 1, ((unsigned long long)__double2ll_rn((double)gq * 1048576.0) << 8) + 1ull);
   }

@@ -742,7 +742,8 @@ int rgm_vae_encode(rgm_vae* h, const float* x, float* moments, int n, void* stre
   Vae* m = reinterpret_cast<Vae*>(h);
   if (n <= 0) return 0;
   if (*static_cast<volatile int*>(m->gn_err_h))
-    return set_error("rgm_vae_encode: an earlier call's GroupNorm-in-epilogue wait gave up (its results are invalid)");
+    return set_error("rgm_vae_encode: an earlier call's in-epilogue GroupNorm failed (a wait gave up, or statistics left "
+                     "the fixed-point range: rgm_vae_gn_timeouts); its results are invalid");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int chunk = m->chunk_tiles < n ? m->chunk_tiles : n;
   if (vae_reserve(m, chunk, 1, st) != 0) return -1;
@@ -763,7 +764,8 @@ int rgm_vae_decode_latents(rgm_vae* h, const float* lat, float scale_factor, flo
   if (Hlat % 16 != 0 || Hlat <= 0) return set_error("rgm_vae_decode_latents: latent length must be a multiple of 16");
   if (roll_ch < 1 || roll_ch > m->out_ch) return set_error("rgm_vae_decode_latents: roll_ch out of range");
   if (*static_cast<volatile int*>(m->gn_err_h))
-    return set_error("rgm_vae_decode_latents: an earlier call's GroupNorm-in-epilogue wait gave up (its results are invalid)");
+    return set_error("rgm_vae_decode_latents: an earlier call's in-epilogue GroupNorm failed (a wait gave up, or "
+                     "statistics left the fixed-point range: rgm_vae_gn_timeouts); its results are invalid");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int total = n_cand * (Hlat / 16);
   const int chunk = m->chunk_tiles < total ? m->chunk_tiles : total;

@@ -308,3 +308,21 @@ def test_upsample_conv_dual_raw_and_normalised_output(cuda, n, H, c):
     torch.cuda.synchronize()
     d = (out.float() - two.float()).abs()
     assert d.max().item() <= 3e-3 * two.float().abs().max().item() + 1e-3, d.max().item()
+
+
+def test_conv_norm_flags_statistics_outside_the_fixed_point_range(cuda):
+    """The in-epilogue GroupNorm accumulates its statistics as 36.20 fixed-point integers: activations with an rms of
+    several hundred over a whole image would wrap them, so the launch must raise the error flag (code 2) instead."""
+    n, H, c = 2, 32, 128
+    g = torch.Generator(device="cpu").manual_seed(3)
+    x = (torch.randn(n, H, H, c, generator=g) * 40.0).to(cuda).half()
+    w = (torch.randn(c, c, 3, 3, generator=g) * 0.5).to(cuda)          # conv output rms ~ 40 * 0.5 * sqrt(1152) ~ 680
+    bias = torch.zeros(c, device=cuda)
+    gamma, beta = torch.ones(c, device=cuda), torch.zeros(c, device=cuda)
+    scratch = torch.zeros(n * 128, device=cuda, dtype=torch.int32)
+    err = torch.zeros(1, device=cuda, dtype=torch.int32)
+    out = torch.empty(n, H, H, c, device=cuda, dtype=torch.float16)
+    _lib.call("rgm_conv_norm_f16", _lib.ptr(x), _lib.ptr(_pack(w, 1)), _lib.ptr(bias), _lib.ptr(gamma), _lib.ptr(beta),
+              None, None, _lib.ptr(out), n, H, H, c, c, 1, 1, _lib.ptr(scratch), _lib.ptr(err), _lib.stream_ptr())
+    torch.cuda.synchronize()
+    assert err.item() == 2

@@ -512,8 +512,11 @@ def run_b200(args):
                 except Exception:
                     tr = None
                 if tr and config == "c3" and B == B_FULL and N == N_FULL:
-                    traffic = tr["traffic_bytes"]
-                    dominant.update(algorithmic_bytes_per_launch=tr["algorithmic_bytes"], traffic_bytes_per_launch=traffic,
+                    # the captures are launches over 128 VAE tiles; a launch of this run covers RGM_VAE_CHUNK tiles
+                    # (default 256) and moves proportionally more
+                    per = int(os.environ.get("RGM_VAE_CHUNK", "256")) / 128.0 if " H1 " not in dn else 1.0
+                    traffic = tr["traffic_bytes"] * per
+                    dominant.update(algorithmic_bytes_per_launch=tr["algorithmic_bytes"] * per, traffic_bytes_per_launch=traffic,
                                     traffic_source="profiles/%s (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum)" % tf)
                     break
         g_ms = sum(v["ms"] for v in gemm.values())

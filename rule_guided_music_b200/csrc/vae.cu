@@ -313,6 +313,7 @@ int run_conv(Ctx& c, const Conv& cv, const __half* x, int H, const __half* resid
     RGM_CUDA_OK(cudaMemsetAsync(c.L->gncount.p, 0, gn_scratch_bytes(c.nt), c.st));
   }
   if (fuse_input_norm) {  // x is RAW: normalise + swish with the current affine inside the operand path (conv_gn.cuh)
+    if (out_norm != nullptr) return set_error("rgm_vae: the consumer-side kernel cannot normalise its own output");
     std::string err;
     if (launch_conv_gn(d, c.ab(), c.st, &err) != cudaSuccess) return set_error("rgm_vae: " + err);
   } else {
@@ -381,8 +382,11 @@ int run_res(Ctx& c, const Res& r, __half* const* buf, Act& a, int H, const Norm*
   const __half* x = buf[a.x];
   if (stats_from_tensor && a.xn < 0)  // x did not come out of a GEMM epilogue (the stems): one direct statistics pass
     RGM_CUDA_OK(launch_gn_stats(x, r.n1.gamma, r.n1.beta, c.ab(), c.nt, HW, r.n1.c, 1e-6f, c.st));
-  const bool e1 = can_fuse_out_norm(c, r.c1, H);  // conv1 writes swish(norm2(conv1(.))) itself: no pass over h
-  const bool f1 = a.xn < 0 && can_fuse_norm(c, r.c1, H), f2 = !e1 && can_fuse_norm(c, r.c2, H);
+  // f1 / f2: the opt-in consumer-side kernel (RGM_CONV_GN=1, conv_gn.cuh) normalises the INPUT of conv1 / conv2 in its
+  // operand path; its epilogue is the plain one, so a convolution that runs on it cannot also normalise its OUTPUT
+  const bool f1 = a.xn < 0 && can_fuse_norm(c, r.c1, H);
+  const bool e1 = !f1 && can_fuse_out_norm(c, r.c1, H);  // conv1 writes swish(norm2(conv1(.))) itself: no pass over h
+  const bool f2 = !e1 && can_fuse_norm(c, r.c2, H);
   int in1 = a.x;  // (f1: the raw tensor, normalised inside the operand path)
   if (a.xn >= 0) {
     in1 = a.xn;
@@ -408,7 +412,8 @@ int run_res(Ctx& c, const Res& r, __half* const* buf, Act& a, int H, const Norm*
   // (not for the 128-feature convolutions: their K = 1152 mainloop on one CTA is shorter than the two-pass epilogue --
   // measured in the step 0.90 ms against 0.58 + 0.22 ms for convolution + normalise pass; the 256- and 512-feature
   // layers on CTA pairs gain 0.06 / 0.015 / 0.006 ms per launch)
-  const bool dual = next != nullptr && want_copy && c.m->gn_dual && r.c2.cout >= c.m->gn_dual_min && can_fuse_out_norm(c, r.c2, H);
+  const bool dual =
+      next != nullptr && want_copy && !f2 && c.m->gn_dual && r.c2.cout >= c.m->gn_dual_min && can_fuse_out_norm(c, r.c2, H);
   const int on = dual ? take_free(used) : -1;  // x, conv2's input and the output are live: the fourth buffer is free
   if (run_conv(c, r.c2, buf[in2], H, resid, buf[o], dual ? nullptr : next, f2, dual ? next : nullptr,
                dual ? buf[on] : nullptr, next_swish))

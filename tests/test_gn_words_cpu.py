@@ -13,8 +13,7 @@ CNT_BITS = 8
 def word(partial):
     """What one warp adds for a partial sum (gn_publish)."""
     q = np.int64(np.rint(np.float64(np.float32(partial)) * FIX))
-    return np.uint64((np.int64(q) << np.int64(CNT_BITS)) + np.int64(1)) if q >= 0 else \
-        np.uint64(np.int64(q << np.int64(CNT_BITS)) + np.int64(1))
+    return ((q << np.int64(CNT_BITS)) + np.int64(1)).astype(np.uint64)  # two's complement: the low byte is the count
 
 
 def unpack(w):

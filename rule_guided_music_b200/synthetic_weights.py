@@ -167,3 +167,40 @@ def make_vae_state_dict(seed=1, **cfg):
             sd[name + ".weight"] = (torch.rand(cout, cin, k, k, generator=g) * 2 - 1) * bound
             sd[name + ".bias"] = (torch.rand(cout, generator=g) * 2 - 1) * bound
     return sd
+
+
+def make_classifier_state_dict(seed=0, depth=4, hidden=384, patch=8, heads=6, in_channels=4, num_classes=9,
+                               mlp_ratio=4.0, std_zero_init=0.02, bias_std=0.02):
+    """State dict of DiTRotaryClassifier, chord=False (dit.py:735-800; `DiTRotary-XS/8-cls` by default).  Same init
+    policy as make_dit_state_dict: Xavier-uniform linears, the tensors the reference zero-inits drawn N(0, 0.02) so
+    that the blocks are not the identity, small non-zero biases, a visible class token."""
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    sd = {}
+    hd = hidden // heads
+    mlp = int(hidden * mlp_ratio)
+
+    def lin(name, out_f, in_f, w_std=None):
+        sd[name + ".weight"] = _xavier(g, out_f, in_f) if w_std is None else torch.randn(out_f, in_f, generator=g) * w_std
+        sd[name + ".bias"] = torch.randn(out_f, generator=g) * bias_std
+
+    lin("x_embedder.MLP.0", 256, in_channels * patch)
+    lin("x_embedder.MLP.2", hidden, 256)
+    lin("t_embedder.mlp.0", hidden, 256, w_std=0.02)
+    lin("t_embedder.mlp.2", hidden, hidden, w_std=0.02)
+    rot = int(hd * 0.5)
+    freqs = 1.0 / (10000 ** (torch.arange(0, rot, 2).float() / rot))
+    sd["rotary_emb.freqs"] = freqs.clone()
+    for i in range(depth):
+        p = f"blocks.{i}."
+        sd[p + "attn.rotary_emb.freqs"] = freqs.clone()
+        lin(p + "attn.qkv", 3 * hidden, hidden)
+        lin(p + "attn.proj", hidden, hidden)
+        lin(p + "mlp.fc1", mlp, hidden)
+        lin(p + "mlp.fc2", hidden, mlp)
+        lin(p + "adaLN_modulation.1", 6 * hidden, hidden, w_std=std_zero_init)
+    sd["cls_token"] = torch.randn(1, 1, hidden, generator=g) * 0.5
+    sd["norm.weight"] = 1.0 + 0.1 * torch.randn(hidden, generator=g)
+    sd["norm.bias"] = 0.05 * torch.randn(hidden, generator=g)
+    lin("classifier_head.0", hidden // 4, hidden)
+    lin("classifier_head.2", num_classes, hidden // 4)
+    return sd

@@ -125,6 +125,26 @@ def golden_dit():
     save("dit", **out)
 
 
+def golden_classifier():
+    """The unmodified DiTRotaryClassifier (dit.py:735-831) and the input-gradient classifier guidance takes of it
+    (condition_functions.grad_nn_zt_xentropy :45-55): groundwork for SURVEY.md 8(f) rank 1."""
+    from guided_diffusion.condition_functions import grad_nn_zt_xentropy
+
+    cfg = gi.CLASSIFIER_CASE
+    w = cfg["weights"]
+    sd = ow.make_classifier_state_dict(**w)
+    model = rdit.DiTRotaryClassifier(input_size=cfg["input_size"], patch_size=w["patch"], in_channels=4,
+                                     hidden_size=w["hidden"], depth=w["depth"], num_heads=w["heads"],
+                                     num_classes=w["num_classes"])
+    model.load_state_dict(sd, strict=True)
+    model.eval()
+    x, t, labels = gi.classifier_inputs(cfg)
+    logits = model(x, t)
+    logits_t0 = model(x, torch.zeros(x.shape[0]))
+    grad = grad_nn_zt_xentropy(x, rule=labels, classifier=model)
+    save("classifier", logits=logits.numpy(), logits_t0=logits_t0.numpy(), xentropy_grad=grad.numpy())
+
+
 def build_ref_vae():
     sd = ow.make_vae_state_dict(seed=gi.VAE_SEED)
     dec = Decoder(**ow.VAE_DDCONFIG)
@@ -434,6 +454,6 @@ def golden_chords():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["schedule", "rules", "dit", "vae", "vae_enc", "collage", "host", "sampler", "sampler_ext", "flagship", "chords"]
+    which = sys.argv[1:] or ["schedule", "rules", "dit", "classifier", "vae", "vae_enc", "collage", "host", "sampler", "sampler_ext", "flagship", "chords"]
     for w in which:
         globals()["golden_" + w]()

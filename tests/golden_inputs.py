@@ -35,6 +35,21 @@ DIT_CASES = {
 }
 
 
+# DiTRotaryClassifier (dit.py:735-831; `DiTRotary-XS/8-cls`, dit.py:951): the classifier-guidance model of SURVEY.md 8(f)
+CLASSIFIER_CASE = dict(input_size=[128, 16], batch=2,
+                       weights=dict(seed=21, depth=4, hidden=384, patch=8, heads=6, num_classes=9))
+
+
+def classifier_inputs(cfg=CLASSIFIER_CASE):
+    g = torch.Generator(device="cpu").manual_seed(2000 + cfg["weights"]["seed"])
+    B = cfg["batch"]
+    H, W = cfg["input_size"]
+    x = torch.randn(B, 4, H, W, generator=g)
+    t = torch.randint(0, 1000, (B,), generator=g)
+    labels = torch.randint(0, cfg["weights"]["num_classes"], (B, 1), generator=g)
+    return x, t, labels
+
+
 def dit_inputs(cfg):
     g = torch.Generator(device="cpu").manual_seed(1000 + cfg["weights"]["seed"])
     B = cfg["batch"]

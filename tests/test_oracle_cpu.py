@@ -124,6 +124,25 @@ def test_dit_against_reference(tag):
         np.testing.assert_allclose(outh, g[tag + "__half"], atol=2e-5, rtol=1e-4)
 
 
+def test_classifier_against_reference():
+    """DiTRotaryClassifier forward (T = 257 with the class token) and the input-gradient of its log-probability that
+    classifier guidance uses (condition_functions.py:45-55), against the unmodified reference."""
+    g = _load("classifier")
+    cfg = gi.CLASSIFIER_CASE
+    sd = ow.make_classifier_state_dict(**cfg["weights"])
+    x, t, labels = gi.classifier_inputs(cfg)
+    kw = _dit_kw(cfg)
+    with torch.no_grad():
+        logits = odit.classifier_forward(sd, x, t, **kw).numpy()
+        logits_t0 = odit.classifier_forward(sd, x, torch.zeros(x.shape[0]), **kw).numpy()
+    assert np.abs(g["logits"]).max() > 1e-2 and np.abs(g["logits"] - g["logits_t0"]).max() > 1e-4  # t matters
+    np.testing.assert_allclose(logits, g["logits"], atol=2e-5, rtol=1e-4)
+    np.testing.assert_allclose(logits_t0, g["logits_t0"], atol=2e-5, rtol=1e-4)
+    grad = odit.classifier_xentropy_grad(sd, x, labels, **kw).numpy()
+    assert np.abs(g["xentropy_grad"]).max() > 1e-4
+    np.testing.assert_allclose(grad, g["xentropy_grad"], atol=2e-6 + 1e-3 * np.abs(g["xentropy_grad"]).max(), rtol=0)
+
+
 def test_vae_against_reference():
     g = _load("vae")
     sd = ow.make_vae_state_dict(seed=gi.VAE_SEED)
